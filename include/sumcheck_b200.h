@@ -1,0 +1,138 @@
+/* sumcheck_b200 — C ABI of the B200-native sumcheck prover path (libsumcheck_b200.so).
+ *
+ * Drop-in boundary for the PROVER path of arkworks-rs/sumcheck (file:line below are relative to the reference
+ * tree).  The reference is pure Rust with #![forbid(unsafe_code)] (src/lib.rs:1) and no FFI of its own, so these
+ * entry points are what a sibling wrapper crate exposing the same names would bind (INTEGRATION.md shows the
+ * `extern "C"` block).  Everything is plain pointers and sizes; no CUDA or torch types appear.
+ *
+ * Field elements: BLS12-381 Fr, `uint64_t[4]` little-endian limbs in Montgomery form (R = 2^256), fully reduced —
+ * exactly the in-memory layout of ark-ff's `Fp<MontBackend<FrConfig,4>,4>`, so `&[Fr]` can be passed as-is.
+ *
+ * Polynomial (ListOfProductsOfPolynomials, src/ml_sumcheck/data_structures.rs:25-35) crosses as:
+ *   tables[n_tables]      host pointers to flattened_ml_extensions[j].evaluations (2^nv elements each)
+ *   coeffs[n_products]    products[k].0
+ *   offsets[n_products+1], indices[offsets[n_products]]   CSR of products[k].1 (indices into tables; repeats allowed)
+ *
+ * Conventions: every function returns SC_OK (0) or a negative SC_ERR_* code; sc_last_error() gives a thread-local
+ * message.  SC_ERR_PANIC_* are the reference's panics: the Rust wrapper turns them back into panic!().
+ * A handle is single-owner and not thread-safe (the reference's input container is !Send).  Calls are synchronous.
+ */
+#ifndef SUMCHECK_B200_H
+#define SUMCHECK_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_OK 0
+#define SC_ERR_PANIC_CONSTANT (-1)        /* prover.rs:50-52  "Attempt to prove a constant."        */
+#define SC_ERR_PANIC_FIRST_ROUND_MSG (-2) /* prover.rs:79-81  "first round should be prover first." */
+#define SC_ERR_PANIC_MISSING_MSG (-3)     /* prover.rs:90-92  "verifier message is empty"           */
+#define SC_ERR_PANIC_NOT_ACTIVE (-4)      /* prover.rs:96-98  "Prover is not active"                */
+#define SC_ERR_BAD_INPUT (-5)             /* data_structures.rs:78,82 asserts; gkr mod.rs:28-29,100-101 asserts */
+#define SC_ERR_CUDA (-10)                 /* CUDA runtime failure -> Error::OtherError (src/error.rs:19) */
+#define SC_ERR_NO_DEVICE (-11)            /* no usable sm_100 device: the library never falls back to the CPU */
+#define SC_ERR_COMM (-12)                 /* multi-GPU exchange failure */
+
+const char *sc_last_error(void);
+int sc_device_count(void); /* number of visible CUDA devices (0 or negative code when none) */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Blake2b512Rng (src/rng.rs:22-81) as plain data, so the wrapper crate's FeedableRNG type can live on either side.
+ * sc_rng_sample_fr = IPForMLSumcheck::sample_round (verifier.rs:128-132 -> ark-ff Fp::rand). */
+typedef struct sc_blake2b512_rng {
+    uint64_t h[8];
+    uint64_t t[2];
+    uint8_t buf[128];
+    uint64_t buflen;
+} sc_blake2b512_rng;
+void sc_rng_setup(sc_blake2b512_rng *rng);                                   /* rng.rs:30-34 */
+void sc_rng_feed_bytes(sc_blake2b512_rng *rng, const uint8_t *b, size_t n);  /* rng.rs:36-41 (bytes = serialize_uncompressed(msg)) */
+void sc_rng_fill_bytes(sc_blake2b512_rng *rng, uint8_t *dest, size_t n);     /* rng.rs:61-80 */
+uint64_t sc_rng_next_u64(sc_blake2b512_rng *rng);                            /* rng.rs:51-55 */
+void sc_rng_sample_fr(sc_blake2b512_rng *rng, uint64_t out[4]);              /* verifier.rs:128-132 */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * ProverState (src/ml_sumcheck/protocol/prover.rs:19-33) resident in HBM. */
+typedef struct sc_prover sc_prover;
+
+/* IPForMLSumcheck::prover_init (prover.rs:49-69): deep-copies every table to device `device` (the caller's buffers
+ * are never written).  nv == 0 -> SC_ERR_PANIC_CONSTANT. */
+int sc_prover_create(sc_prover **out, uint32_t nv, uint32_t n_tables, const uint64_t *const *tables,
+                     uint32_t n_products, const uint64_t *coeffs, const uint32_t *offsets, const uint32_t *indices,
+                     int device);
+/* Same, but the tables are ALREADY device pointers on `device` (e.g. produced by an earlier GPU stage); they are
+ * read, never written, and must stay alive until the handle is destroyed or reset no longer needs them. */
+int sc_prover_create_device(sc_prover **out, uint32_t nv, uint32_t n_tables, const uint64_t *const *d_tables,
+                            uint32_t n_products, const uint64_t *coeffs, const uint32_t *offsets,
+                            const uint32_t *indices, int device);
+void sc_prover_destroy(sc_prover *p);
+/* Rewind to round 0 on the tables given at creation (they are kept pristine in HBM); for repeated proofs. */
+int sc_prover_reset(sc_prover *p);
+
+/* IPForMLSumcheck::prove_round (prover.rs:74-153).  r_or_null = Some(VerifierMsg{randomness}) / None.
+ * evals_out receives ProverMsg.evaluations: (max_multiplicands+1) x 4 u64, P(0)..P(d). */
+int sc_prove_round(sc_prover *p, const uint64_t *r_or_null, uint64_t *evals_out);
+
+uint32_t sc_prover_max_multiplicands(const sc_prover *p); /* ProverState.max_multiplicands */
+uint32_t sc_prover_num_vars(const sc_prover *p);          /* ProverState.num_vars          */
+uint32_t sc_prover_round(const sc_prover *p);             /* ProverState.round             */
+/* ProverState.randomness (prover.rs:21): copies min(len, cap) elements, returns len. */
+uint32_t sc_prover_randomness(const sc_prover *p, uint64_t *out, uint32_t cap);
+/* `prover_state.randomness.push(r)` (ml_sumcheck/mod.rs:65-67): records the final challenge WITHOUT folding — for
+ * wrappers that run the round loop themselves; sc_ml_prove does it internally. */
+int sc_prover_push_randomness(sc_prover *p, const uint64_t r[4]);
+/* ProverState.flattened_ml_extensions[j].evaluations at the current round (length 2^(nv-round+1), or 2^nv at
+ * round 0): copies it to `out` (host) and stores its length in *len_out. */
+int sc_prover_table(const sc_prover *p, uint32_t j, uint64_t *out, uint64_t cap_elems, uint64_t *len_out);
+
+/* MLSumcheck::prove_as_subprotocol (src/ml_sumcheck/mod.rs:50-70) on a prover at round 0: feeds PolynomialInfo,
+ * runs all rounds with the transcript, pushes the last challenge.  `rng` is updated in place (as &mut fs_rng).
+ * evals_out: nv*(d+1)*4 u64 = Proof<F>; randomness_out (nullable): nv*4 u64 = ProverState.randomness. */
+int sc_ml_prove(sc_prover *p, sc_blake2b512_rng *rng, uint64_t *evals_out, uint64_t *randomness_out);
+
+/* MLSumcheck::prove (mod.rs:42-45): fresh Blake2b512Rng::setup(), host tables in, proof out. */
+int sc_ml_prove_oneshot(uint32_t nv, uint32_t n_tables, const uint64_t *const *tables, uint32_t n_products,
+                        const uint64_t *coeffs, const uint32_t *offsets, const uint32_t *indices, int device,
+                        uint64_t *evals_out, uint64_t *randomness_out);
+
+/* ark-serialize bytes of Proof<F> = Vec<ProverMsg<F>> (what `proof.serialize_uncompressed` yields): returns the
+ * byte count 8 + nv*(8 + 32*(d+1)); writes when out != NULL. */
+size_t sc_serialize_proof(const uint64_t *evals, uint32_t nv, uint32_t d, uint8_t *out);
+
+/* Per-round device timings of the last sc_ml_prove on this handle (ms, CUDA events on the launching stream):
+ * copies min(nv, cap) values, returns nv. Kernel-only; excludes transcript/host time. */
+uint32_t sc_prover_round_times_ms(const sc_prover *p, float *out, uint32_t cap);
+/* Number of kernels launched by this handle since creation/reset. */
+uint64_t sc_prover_launch_count(const sc_prover *p);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * GKRRoundSumcheck (src/gkr_round_sumcheck/mod.rs).  f1: SparseMultilinearExtension over 3*dim variables as nnz
+ * (index, value) pairs with unique indices (its BTreeMap); index bits are g | x | y, least significant first
+ * (gkr test.rs:47-55).  f2, f3: dense, 2^dim elements.  g: dim elements. */
+
+/* initialize_phase_one (mod.rs:22-42).  h_g_out: 2^dim elements.  f1_g (f1 fixed at g, a sparse MLE over 2*dim
+ * variables) is returned as sorted unique (index,value) pairs: capacity nnz each; *nnz_g_out = its length. */
+int sc_gkr_initialize_phase_one(uint32_t dim, uint64_t nnz, const uint64_t *f1_idx, const uint64_t *f1_val,
+                                const uint64_t *f3, const uint64_t *g, int device, uint64_t *h_g_out,
+                                uint64_t *f1g_idx_out, uint64_t *f1g_val_out, uint64_t *nnz_g_out);
+/* initialize_phase_two (mod.rs:57-63): f1_g fixed at u, as a dense 2^dim table. */
+int sc_gkr_initialize_phase_two(uint32_t dim, uint64_t nnz_g, const uint64_t *f1g_idx, const uint64_t *f1g_val,
+                                const uint64_t *u, int device, uint64_t *f1_gu_out);
+/* start_phase1_sumcheck (mod.rs:45-54) / start_phase2_sumcheck (mod.rs:66-82): ProverState for 1*(a*b) resp.
+ * 1*(f1_gu * (f2_u*f3)). */
+int sc_gkr_start_phase1_sumcheck(sc_prover **out, uint32_t dim, const uint64_t *h_g, const uint64_t *f2, int device);
+int sc_gkr_start_phase2_sumcheck(sc_prover **out, uint32_t dim, const uint64_t *f1_gu, const uint64_t *f3,
+                                 const uint64_t f2_u[4], int device);
+/* GKRRoundSumcheck::prove (mod.rs:93-139) with the concrete Blake2b512Rng.  phase1_out/phase2_out: dim*3*4 u64
+ * (GKRProof.phase{1,2}_sumcheck_msgs); u_out/v_out nullable: dim*4 u64. */
+int sc_gkr_prove(sc_blake2b512_rng *rng, uint32_t dim, uint64_t nnz, const uint64_t *f1_idx, const uint64_t *f1_val,
+                 const uint64_t *f2, const uint64_t *f3, const uint64_t *g, int device, uint64_t *phase1_out,
+                 uint64_t *phase2_out, uint64_t *u_out, uint64_t *v_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,415 @@
+"""Host-side mirror of the reference's prover API (same names, argument meaning and error behaviour), over the C ABI.
+
+Reference (paths relative to arkworks-rs/sumcheck):
+  ListOfProductsOfPolynomials / PolynomialInfo   src/ml_sumcheck/data_structures.rs:25-109
+  IPForMLSumcheck.prover_init / prove_round       src/ml_sumcheck/protocol/prover.rs:49,74
+  MLSumcheck.prove / prove_as_subprotocol         src/ml_sumcheck/mod.rs:42,50
+  Blake2b512Rng (FeedableRNG)                     src/rng.rs:11-81
+  GKRRoundSumcheck.prove + phase initialisers     src/gkr_round_sumcheck/mod.rs:22-139
+
+Field elements are numpy ``uint64`` arrays whose last axis holds the 4 little-endian Montgomery limbs of a
+BLS12-381 Fr element — the memory layout of ark-ff's ``Fr``.  A dense multilinear extension is a ``[2^nv, 4]`` array.
+Where the reference panics this module raises ``Panic``; where it returns ``Err`` it raises ``SumcheckError``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import U8P, U32P, U64P, RngState
+
+P_MODULUS = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+FR_ONE = np.array([0x00000001FFFFFFFE, 0x5884B7FA00034802, 0x998C4FEFECBC4FF5, 0x1824B159ACC5056F], dtype=np.uint64)
+
+
+class Panic(Exception):
+    """The reference panics here (misuse of the prover state machine, prover.rs:50-52,79-81,90-92,96-98)."""
+
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+class SumcheckError(Exception):
+    """crate::Error (src/error.rs:7-19) — device/driver failures map to Error::OtherError."""
+
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def _check(rc):
+    if rc == 0:
+        return
+    msg = capi.lib().sc_last_error().decode()
+    if -4 <= rc <= -1:
+        raise Panic(rc, msg)
+    raise SumcheckError(rc, msg)
+
+
+def _p64(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(U64P)
+
+
+def _p32(a):
+    assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(U32P)
+
+
+def _elems(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+# ---------------------------------------------------------------------------------------------- transcript
+class Blake2b512Rng:
+    """FeedableRNG over Blake2b-512 (src/rng.rs:22-81); state is the plain-data sc_blake2b512_rng."""
+
+    def __init__(self):
+        self.state = RngState()
+        capi.lib().sc_rng_setup(C.byref(self.state))
+
+    @classmethod
+    def setup(cls):  # rng.rs:30-34
+        return cls()
+
+    def feed(self, msg):
+        """rng.rs:36-41.  `msg` is bytes already in ark-serialize form, or an object with serialize_uncompressed()."""
+        b = msg if isinstance(msg, (bytes, bytearray)) else msg.serialize_uncompressed()
+        capi.lib().sc_rng_feed_bytes(C.byref(self.state), bytes(b), len(b))
+
+    def fill_bytes(self, n):  # rng.rs:57-80
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        capi.lib().sc_rng_fill_bytes(C.byref(self.state), out.ctypes.data_as(U8P), n)
+        return out[:n].tobytes()
+
+    def next_u64(self):  # rng.rs:51-55
+        return int(capi.lib().sc_rng_next_u64(C.byref(self.state)))
+
+    def next_u32(self):  # rng.rs:45-49
+        return int.from_bytes(self.fill_bytes(4), "little")
+
+
+# ---------------------------------------------------------------------------------------------- data structures
+class PolynomialInfo:
+    """data_structures.rs:47-55."""
+
+    def __init__(self, max_multiplicands, num_variables):
+        self.max_multiplicands = max_multiplicands
+        self.num_variables = num_variables
+
+    def serialize_uncompressed(self):
+        return self.max_multiplicands.to_bytes(8, "little") + self.num_variables.to_bytes(8, "little")
+
+
+class ListOfProductsOfPolynomials:
+    """data_structures.rs:25-96.  Tables are de-duplicated by object identity, like the reference's Rc pointers."""
+
+    def __init__(self, num_variables):
+        self.max_multiplicands = 0
+        self.num_variables = num_variables
+        self.products = []                 # [(coefficient[4], [indices])]
+        self.flattened_ml_extensions = []  # unique tables
+        self._lookup = {}                  # id(table) -> index   (raw_pointers_lookup_table)
+
+    @classmethod
+    def new(cls, num_variables):  # data_structures.rs:59-67
+        return cls(num_variables)
+
+    def info(self):  # data_structures.rs:39-44
+        return PolynomialInfo(self.max_multiplicands, self.num_variables)
+
+    def add_product(self, product, coefficient):  # data_structures.rs:71-96
+        product = list(product)
+        assert len(product) > 0
+        self.max_multiplicands = max(self.max_multiplicands, len(product))
+        indexed = []
+        for m in product:
+            assert m.dtype == np.uint64 and m.shape == (1 << self.num_variables, 4), \
+                "product has a multiplicand with wrong number of variables"
+            key = id(m)
+            if key in self._lookup:
+                indexed.append(self._lookup[key])
+            else:
+                self._lookup[key] = len(self.flattened_ml_extensions)
+                self.flattened_ml_extensions.append(np.ascontiguousarray(m))
+                if self.flattened_ml_extensions[-1] is not m:  # keep identity stable for later look-ups
+                    self._lookup[id(self.flattened_ml_extensions[-1])] = self._lookup[key]
+                indexed.append(self._lookup[key])
+        self.products.append((_elems(coefficient), indexed))
+
+    # what crosses the C ABI
+    def _csr(self):
+        coeffs = np.ascontiguousarray(np.stack([c for c, _ in self.products])) if self.products else np.zeros((0, 4), np.uint64)
+        offs, idx = [0], []
+        for _, ix in self.products:
+            idx.extend(ix)
+            offs.append(len(idx))
+        return coeffs, np.array(offs, dtype=np.uint32), np.array(idx if idx else [0], dtype=np.uint32)
+
+
+class ProverMsg:
+    """prover.rs:14-17."""
+
+    def __init__(self, evaluations):
+        self.evaluations = evaluations  # [d+1, 4]
+
+    def serialize_uncompressed(self):
+        n = self.evaluations.shape[0]
+        b = _serialize_msgs(self.evaluations.reshape(1, n, 4))
+        return b[8:]  # strip the outer Vec<ProverMsg> length
+
+
+class VerifierMsg:
+    """verifier.rs:11-15."""
+
+    def __init__(self, randomness):
+        self.randomness = _elems(randomness)
+
+
+def _serialize_msgs(evals):
+    """ark-serialize of Vec<ProverMsg<F>> for evals[nv, d+1, 4]."""
+    evals = np.ascontiguousarray(evals, dtype=np.uint64)
+    nv, dp1 = evals.shape[0], evals.shape[1]
+    L = capi.lib()
+    n = L.sc_serialize_proof(_p64(evals), nv, dp1 - 1, None)
+    out = np.zeros(n, dtype=np.uint8)
+    got = L.sc_serialize_proof(_p64(evals), nv, dp1 - 1, out.ctypes.data_as(U8P))
+    if got != n:
+        raise SumcheckError(-10, "sc_serialize_proof failed: " + L.sc_last_error().decode())
+    return out.tobytes()
+
+
+class ProverState:
+    """prover.rs:19-33, resident in HBM.  Public fields of the reference are properties here."""
+
+    def __init__(self, handle, poly=None):
+        self._h = handle
+        self._poly = poly  # keeps host tables alive / gives list_of_products
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            capi.lib().sc_prover_destroy(h)
+
+    @property
+    def round(self):
+        return int(capi.lib().sc_prover_round(self._h))
+
+    @property
+    def num_vars(self):
+        return int(capi.lib().sc_prover_num_vars(self._h))
+
+    @property
+    def max_multiplicands(self):
+        return int(capi.lib().sc_prover_max_multiplicands(self._h))
+
+    @property
+    def list_of_products(self):
+        return list(self._poly.products) if self._poly is not None else None
+
+    @property
+    def randomness(self):
+        L = capi.lib()
+        n = L.sc_prover_randomness(self._h, None, 0)
+        out = np.zeros((max(n, 1), 4), dtype=np.uint64)
+        L.sc_prover_randomness(self._h, _p64(out), n)
+        return out[:n]
+
+    def table(self, j):
+        L = capi.lib()
+        ln = C.c_uint64()
+        _check(L.sc_prover_table(self._h, j, None, 0, C.byref(ln)))
+        out = np.zeros((ln.value, 4), dtype=np.uint64)
+        _check(L.sc_prover_table(self._h, j, _p64(out), ln.value, C.byref(ln)))
+        return out
+
+    @property
+    def flattened_ml_extensions(self):
+        n = len(self._poly.flattened_ml_extensions) if self._poly is not None else 2
+        return [self.table(j) for j in range(n)]
+
+    def reset(self):
+        _check(capi.lib().sc_prover_reset(self._h))
+
+    def round_times_ms(self):
+        nv = self.num_vars
+        out = np.zeros(nv, dtype=np.float32)
+        capi.lib().sc_prover_round_times_ms(self._h, out.ctypes.data_as(capi.F32P), nv)
+        return out
+
+    def launch_count(self):
+        return int(capi.lib().sc_prover_launch_count(self._h))
+
+
+def _create(poly, device):
+    coeffs, offsets, indices = poly._csr()
+    T = len(poly.flattened_ml_extensions)
+    tabs = (C.c_void_p * max(T, 1))(*[t.ctypes.data for t in poly.flattened_ml_extensions])
+    h = C.c_void_p()
+    _check(capi.lib().sc_prover_create(C.byref(h), poly.num_variables, T, tabs, len(poly.products),
+                                       _p64(coeffs) if len(poly.products) else None, _p32(offsets), _p32(indices), device))
+    return ProverState(h, poly)
+
+
+class IPForMLSumcheck:
+    """protocol/mod.rs:10-13 marker + prover.rs / verifier.rs:128 entry points on the prover path."""
+
+    @staticmethod
+    def prover_init(polynomial, device=0):  # prover.rs:49-69
+        return _create(polynomial, device)
+
+    @staticmethod
+    def prove_round(prover_state, v_msg):  # prover.rs:74-153
+        d = prover_state.max_multiplicands
+        out = np.zeros((d + 1, 4), dtype=np.uint64)
+        r = _p64(v_msg.randomness) if v_msg is not None else None
+        _check(capi.lib().sc_prove_round(prover_state._h, r, _p64(out)))
+        return ProverMsg(out)
+
+    @staticmethod
+    def sample_round(rng):  # verifier.rs:128-132
+        out = np.zeros(4, dtype=np.uint64)
+        capi.lib().sc_rng_sample_fr(C.byref(rng.state), _p64(out))
+        return VerifierMsg(out)
+
+
+def _fr_add_mont(a, b):
+    """a + b mod p on Montgomery limbs (addition is representation-agnostic)."""
+    x = sum(int(a[i]) << (64 * i) for i in range(4)) + sum(int(b[i]) << (64 * i) for i in range(4))
+    x %= P_MODULUS
+    return np.array([(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+class MLSumcheck:
+    """src/ml_sumcheck/mod.rs:19-70 (prover side)."""
+
+    @staticmethod
+    def extract_sum(proof):  # mod.rs:26-28
+        return _fr_add_mont(proof[0].evaluations[0], proof[0].evaluations[1])
+
+    @staticmethod
+    def prove(polynomial, device=0):  # mod.rs:42-45
+        rng = Blake2b512Rng.setup()
+        proof, _ = MLSumcheck.prove_as_subprotocol(rng, polynomial, device)
+        return proof
+
+    @staticmethod
+    def prove_as_subprotocol(fs_rng, polynomial, device=0):  # mod.rs:50-70
+        if isinstance(fs_rng, Blake2b512Rng):
+            state = _create(polynomial, device)
+            nv, d = polynomial.num_variables, state.max_multiplicands
+            evals = np.zeros((nv, d + 1, 4), dtype=np.uint64)
+            _check(capi.lib().sc_ml_prove(state._h, C.byref(fs_rng.state), _p64(evals), None))
+            return [ProverMsg(evals[i]) for i in range(nv)], state
+        # generic FeedableRNG: the round loop stays on the host, one C call per round
+        fs_rng.feed(polynomial.info().serialize_uncompressed())
+        state = IPForMLSumcheck.prover_init(polynomial, device)
+        v_msg, msgs = None, []
+        for _ in range(polynomial.num_variables):
+            pm = IPForMLSumcheck.prove_round(state, v_msg)
+            fs_rng.feed(pm.serialize_uncompressed())
+            msgs.append(pm)
+            v_msg = IPForMLSumcheck.sample_round(fs_rng)
+        # mod.rs:65-67 pushes the last challenge without folding
+        _check(capi.lib().sc_prover_push_randomness(state._h, _p64(v_msg.randomness)))
+        return msgs, state
+
+    @staticmethod
+    def serialize_proof(proof):
+        return _serialize_msgs(np.stack([m.evaluations for m in proof]))
+
+
+# ---------------------------------------------------------------------------------------------- GKR
+class SparseMultilinearExtension:
+    """ark-poly SparseMultilinearExtension as (unique indices, values)."""
+
+    def __init__(self, num_vars, indices, values):
+        self.num_vars = num_vars
+        self.indices = np.ascontiguousarray(indices, dtype=np.uint64)
+        self.values = _elems(values).reshape(-1, 4)
+        assert self.indices.shape[0] == self.values.shape[0]
+
+
+class GKRProof:
+    """gkr_round_sumcheck/data_structures.rs:9-20."""
+
+    def __init__(self, phase1_sumcheck_msgs, phase2_sumcheck_msgs):
+        self.phase1_sumcheck_msgs = phase1_sumcheck_msgs
+        self.phase2_sumcheck_msgs = phase2_sumcheck_msgs
+
+    def extract_sum(self):
+        return _fr_add_mont(self.phase1_sumcheck_msgs[0].evaluations[0], self.phase1_sumcheck_msgs[0].evaluations[1])
+
+
+def _dim_of(table):
+    n = table.shape[0]
+    assert n & (n - 1) == 0
+    return n.bit_length() - 1
+
+
+def initialize_phase_one(f1, f3, g, device=0):
+    """mod.rs:22-42 -> (h_g dense, f1 fixed at g as SparseMultilinearExtension)."""
+    f3, g = _elems(f3), _elems(g)
+    dim = _dim_of(f3)
+    assert f1.num_vars == dim * 3 and g.shape[0] == dim
+    nnz = f1.indices.shape[0]
+    h_g = np.zeros((1 << dim, 4), dtype=np.uint64)
+    gi = np.zeros(max(nnz, 1), dtype=np.uint64)
+    gv = np.zeros((max(nnz, 1), 4), dtype=np.uint64)
+    n_g = C.c_uint64()
+    _check(capi.lib().sc_gkr_initialize_phase_one(dim, nnz, _p64(f1.indices), _p64(f1.values), _p64(f3), _p64(g), device,
+                                                  _p64(h_g), _p64(gi), _p64(gv), C.byref(n_g)))
+    return h_g, SparseMultilinearExtension(2 * dim, gi[:n_g.value].copy(), gv[:n_g.value].copy())
+
+
+def initialize_phase_two(f1_g, u, device=0):
+    """mod.rs:57-63 -> f1 fixed at g||u as a dense table."""
+    u = _elems(u)
+    dim = u.shape[0]
+    assert dim * 2 == f1_g.num_vars
+    out = np.zeros((1 << dim, 4), dtype=np.uint64)
+    _check(capi.lib().sc_gkr_initialize_phase_two(dim, f1_g.indices.shape[0], _p64(f1_g.indices), _p64(f1_g.values), _p64(u),
+                                                  device, _p64(out)))
+    return out
+
+
+def start_phase1_sumcheck(h_g, f2, device=0):
+    """mod.rs:45-54."""
+    h_g, f2 = _elems(h_g), _elems(f2)
+    dim = _dim_of(h_g)
+    assert _dim_of(f2) == dim
+    h = C.c_void_p()
+    _check(capi.lib().sc_gkr_start_phase1_sumcheck(C.byref(h), dim, _p64(h_g), _p64(f2), device))
+    return ProverState(h)
+
+
+def start_phase2_sumcheck(f1_gu, f3, f2_u, device=0):
+    """mod.rs:66-82."""
+    f1_gu, f3, f2_u = _elems(f1_gu), _elems(f3), _elems(f2_u)
+    dim = _dim_of(f1_gu)
+    assert _dim_of(f3) == dim
+    h = C.c_void_p()
+    _check(capi.lib().sc_gkr_start_phase2_sumcheck(C.byref(h), dim, _p64(f1_gu), _p64(f3), _p64(f2_u), device))
+    return ProverState(h)
+
+
+class GKRRoundSumcheck:
+    """src/gkr_round_sumcheck/mod.rs:85-139 (prover side)."""
+
+    @staticmethod
+    def prove(rng, f1, f2, f3, g, device=0, return_challenges=False):
+        f2, f3, g = _elems(f2), _elems(f3), _elems(g)
+        dim = _dim_of(f2)
+        assert f1.num_vars == 3 * dim and _dim_of(f3) == dim  # mod.rs:100-101
+        m1 = np.zeros((dim, 3, 4), dtype=np.uint64)
+        m2 = np.zeros((dim, 3, 4), dtype=np.uint64)
+        u = np.zeros((dim, 4), dtype=np.uint64)
+        v = np.zeros((dim, 4), dtype=np.uint64)
+        if not isinstance(rng, Blake2b512Rng):
+            raise SumcheckError(-5, "the device path binds the concrete Blake2b512Rng; drive the phases via "
+                                    "initialize_phase_*/start_phase*_sumcheck + prove_round for other FeedableRNGs")
+        _check(capi.lib().sc_gkr_prove(C.byref(rng.state), dim, f1.indices.shape[0], _p64(f1.indices), _p64(f1.values),
+                                       _p64(f2), _p64(f3), _p64(g), device, _p64(m1), _p64(m2), _p64(u), _p64(v)))
+        proof = GKRProof([ProverMsg(m1[i]) for i in range(dim)], [ProverMsg(m2[i]) for i in range(dim)])
+        return (proof, u, v) if return_challenges else proof

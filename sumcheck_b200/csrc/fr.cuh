@@ -1,0 +1,209 @@
+// BLS12-381 scalar field Fr on sm_100a: 8 x u32 limbs, Montgomery form R = 2^256, values always fully reduced —
+// bit-identical to ark-ff's Fp<MontBackend<FrConfig,4>,4> in memory (4 x u64 LE), which is what the reference's
+// tables hold (ml_sumcheck/protocol/prover.rs:26 `flattened_ml_extensions`).  Field arithmetic is exact and the
+// representation canonical, so any evaluation order reproduces the reference's limbs.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "fr_asm.cuh"
+
+namespace fr {
+
+struct Fr {
+    uint32_t l[8];
+};
+
+// p, little-endian 32-bit limbs.  p[0] = 1 and -p^-1 mod 2^32 = 0xffffffff.
+#define FR_P0 0x00000001u
+#define FR_P1 0xffffffffu
+#define FR_P2 0xfffe5bfeu
+#define FR_P3 0x53bda402u
+#define FR_P4 0x09a1d805u
+#define FR_P5 0x3339d808u
+#define FR_P6 0x299d7d48u
+#define FR_P7 0x73eda753u
+
+__device__ __forceinline__ Fr zero() {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = 0;
+    return r;
+}
+// R mod p  (Montgomery form of 1)
+__device__ __forceinline__ Fr one() {
+    Fr r = {{0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u}};
+    return r;
+}
+
+// 256-bit vector accesses (LDG.E.256 / STG.E.256 on sm_100): one instruction per element.
+__device__ __forceinline__ Fr load(const uint32_t* p) {
+    Fr r;
+    asm volatile("ld.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+                 : "l"(p));
+    return r;
+}
+// streaming read: read-only path, do not keep in L1 (every table element is consumed exactly once per round)
+__device__ __forceinline__ Fr load_stream(const uint32_t* p) {
+    Fr r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void store(uint32_t* p, const Fr& v) {
+    asm volatile("st.global.v8.u32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(v.l[0]), "r"(v.l[1]), "r"(v.l[2]), "r"(v.l[3]),
+                 "r"(v.l[4]), "r"(v.l[5]), "r"(v.l[6]), "r"(v.l[7]), "l"(p)
+                 : "memory");
+}
+
+__device__ __forceinline__ bool is_zero(const Fr& a) {
+    return (a.l[0] | a.l[1] | a.l[2] | a.l[3] | a.l[4] | a.l[5] | a.l[6] | a.l[7]) == 0;
+}
+__device__ __forceinline__ bool eq(const Fr& a, const Fr& b) {
+    uint32_t d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d |= a.l[i] ^ b.l[i];
+    return d == 0;
+}
+
+// r = a - p if a >= p else a      (a < 2p)
+__device__ __forceinline__ Fr reduce_once(const Fr& a) {
+    Fr s;
+    uint32_t borrow;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;\n\t"
+        : "=r"(s.l[0]), "=r"(s.l[1]), "=r"(s.l[2]), "=r"(s.l[3]), "=r"(s.l[4]), "=r"(s.l[5]), "=r"(s.l[6]), "=r"(s.l[7]),
+          "=r"(borrow)
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]), "r"(FR_P0),
+          "r"(FR_P1), "r"(FR_P2), "r"(FR_P3), "r"(FR_P4), "r"(FR_P5), "r"(FR_P6), "r"(FR_P7));
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = borrow ? a.l[i] : s.l[i];
+    return r;
+}
+
+__device__ __forceinline__ Fr add(const Fr& a, const Fr& b) {
+    Fr t;  // a + b < 2p < 2^256: no carry out
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;\n\t"
+        : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]), "=r"(t.l[6]), "=r"(t.l[7])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]), "r"(b.l[0]),
+          "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    return reduce_once(t);
+}
+
+__device__ __forceinline__ Fr sub(const Fr& a, const Fr& b) {
+    Fr t;
+    uint32_t borrow;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;\n\t"
+        : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]), "=r"(t.l[6]), "=r"(t.l[7]),
+          "=r"(borrow)
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]), "r"(b.l[0]),
+          "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    // borrow = 0xffffffff when a < b: add p back (masked)
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;\n\t"
+        : "+r"(t.l[0]), "+r"(t.l[1]), "+r"(t.l[2]), "+r"(t.l[3]), "+r"(t.l[4]), "+r"(t.l[5]), "+r"(t.l[6]), "+r"(t.l[7])
+        : "r"(FR_P0 & borrow), "r"(FR_P1 & borrow), "r"(FR_P2 & borrow), "r"(FR_P3 & borrow), "r"(FR_P4 & borrow),
+          "r"(FR_P5 & borrow), "r"(FR_P6 & borrow), "r"(FR_P7 & borrow));
+    return t;
+}
+
+// Montgomery product a*b*2^-256 mod p: 64 IMAD.WIDE for the product + 56 for the reduction.
+__device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) {
+    uint32_t ev[16], od[16];
+    mul_wide_eo(ev, od, a.l, b.l);
+    uint32_t c = redc_eo(ev, od);
+    // quotient = sum_{k=8..15} (ev[k] + od[k-1]) 2^(32(k-8)) + c   (< 2p, fits 8 limbs)
+    Fr t;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;\n\t"
+        : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]), "=r"(t.l[6]), "=r"(t.l[7])
+        : "r"(ev[8]), "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]), "r"(od[7]),
+          "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.u32 %7, %7, 0;\n\t"
+        : "+r"(t.l[0]), "+r"(t.l[1]), "+r"(t.l[2]), "+r"(t.l[3]), "+r"(t.l[4]), "+r"(t.l[5]), "+r"(t.l[6]), "+r"(t.l[7])
+        : "r"(c));
+    return reduce_once(t);
+}
+
+// Reference formulation in plain C (32-bit limbs, 64-bit accumulators); used by the micro-benchmark as a baseline.
+__device__ __forceinline__ Fr mul_c64(const Fr& a, const Fr& b) {
+    const uint32_t P[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    uint32_t t[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            c += (uint64_t)a.l[j] * b.l[i] + t[j];
+            t[j] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[8];
+        t[8] = (uint32_t)c;
+        t[9] = (uint32_t)(c >> 32);
+        uint32_t m = 0u - t[0];
+        c = (uint64_t)m * P[0] + t[0];
+        c >>= 32;
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+            c += (uint64_t)m * P[j] + t[j];
+            t[j - 1] = (uint32_t)c;
+            c >>= 32;
+        }
+        c += t[8];
+        t[7] = (uint32_t)c;
+        t[8] = t[9] + (uint32_t)(c >> 32);
+    }
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = t[i];
+    return reduce_once(r);
+}
+
+}  // namespace fr

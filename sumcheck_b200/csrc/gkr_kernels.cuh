@@ -1,0 +1,150 @@
+// GKR round-function initialisers (/root/reference/src/gkr_round_sumcheck/mod.rs:22-63) and small helpers.
+//
+// The reference walks BTreeMap/HashMap entries and scatter-accumulates into dense vectors.  On the GPU the
+// scatter `dst[key] += value (mod p)` has no native atomic, so each destination is kept as 8 x u64 lanes holding
+// plain integer sums of the 32-bit limbs (native 64-bit atomicAdd; up to 2^32 addends cannot overflow a lane) and
+// a second pass carry-propagates and reduces mod p.  Integer sums commute, so the result is order-independent and
+// equals the reference's value exactly.
+#pragma once
+#include <cstdint>
+
+#include "fr.cuh"
+
+namespace sck {
+
+using fr::Fr;
+
+__device__ __forceinline__ Fr fr_R2() {  // R^2 mod p: mul(x, R2) = x*R mod p
+    Fr r = {{0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u}};
+    return r;
+}
+
+// eq[b] = prod_j (b_j ? g_j : 1 - g_j)  — ark-poly precompute_eq (external), bit j of b <-> g[j]
+__global__ void __launch_bounds__(128) eq_table_kernel(const uint32_t* g, uint32_t dim, uint32_t* out) {
+    const unsigned long long n = 1ull << dim;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < n;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        Fr acc = fr::one();
+        for (uint32_t j = 0; j < dim; j++) {
+            Fr gj = fr::load(g + 8 * j);
+            Fr f = ((b >> j) & 1) ? gj : fr::sub(fr::one(), gj);
+            acc = (j == 0) ? f : fr::mul(acc, f);
+        }
+        fr::store(out + b * 8, acc);
+    }
+}
+
+__device__ __forceinline__ void lanes_add(unsigned long long* lanes, const Fr& v) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) atomicAdd(lanes + i, (unsigned long long)v.l[i]);
+}
+
+// initialize_phase_one (mod.rs:30-38), per nonzero of f1 with idx = z | x << dim | y << 2dim:
+//   w = eq_g[z] * v            (f1.fix_variables(g): f1_g[idx >> dim] += eq_g[idx & mask] * v)
+//   hg_lanes[x] += w * f3[y]   (a_hg[x] += f1_g[xy] * f3[y])
+// w is kept (keyed by xy = idx >> dim) for phase two.
+__global__ void __launch_bounds__(128) gkr_phase1_scatter_kernel(const unsigned long long* f1_idx, const uint32_t* f1_val,
+                                                                unsigned long long nnz, uint32_t dim, const uint32_t* eq_g,
+                                                                const uint32_t* f3, uint32_t* w_out,
+                                                                unsigned long long* hg_lanes) {
+    const unsigned long long mask = (1ull << dim) - 1;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long idx = f1_idx[i];
+        const unsigned long long z = idx & mask, x = (idx >> dim) & mask, y = idx >> (2 * dim);
+        Fr w = fr::mul(fr::load(eq_g + z * 8), fr::load(f1_val + i * 8));
+        fr::store(w_out + i * 8, w);
+        if (hg_lanes) lanes_add(hg_lanes + x * 8, fr::mul(w, fr::load(f3 + y * 8)));
+    }
+}
+
+// initialize_phase_two (mod.rs:57-63): f1_gu[y] += eq_u[x] * f1_g[x | y << dim]; keys are xy (already >> dim when
+// `shift` = 0, or the original f1 index with shift = dim).
+__global__ void __launch_bounds__(128) gkr_phase2_scatter_kernel(const unsigned long long* keys, uint32_t shift,
+                                                                const uint32_t* w, unsigned long long nnz, uint32_t dim,
+                                                                const uint32_t* eq_u, unsigned long long* out_lanes) {
+    const unsigned long long mask = (1ull << dim) - 1;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long xy = keys[i] >> shift;
+        const unsigned long long x = xy & mask, y = xy >> dim;
+        lanes_add(out_lanes + y * 8, fr::mul(fr::load(eq_u + x * 8), fr::load(w + i * 8)));
+    }
+}
+
+// lanes (8 x u64 integer sums of limbs) -> fully reduced field element
+__device__ __forceinline__ Fr lanes_to_fr(const unsigned long long* lanes) {
+    Fr lo;
+    unsigned long long c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        unsigned long long s = lanes[i];
+        unsigned long long lo32 = (s & 0xffffffffull) + (c & 0xffffffffull);
+        lo.l[i] = (uint32_t)lo32;
+        c = (s >> 32) + (c >> 32) + (lo32 >> 32);
+    }
+    // value = lo + c * 2^256 with lo < 2^256 < 3p: two conditional subtractions, then add c*R mod p
+    lo = fr::reduce_once(fr::reduce_once(lo));
+    if (c != 0) {
+        Fr craw = fr::zero();
+        craw.l[0] = (uint32_t)c;
+        craw.l[1] = (uint32_t)(c >> 32);
+        lo = fr::add(lo, fr::mul(craw, fr_R2()));
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) lanes_normalise_kernel(const unsigned long long* lanes, unsigned long long n,
+                                                             uint32_t* out) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        fr::store(out + i * 8, lanes_to_fr(lanes + i * 8));
+}
+
+// out[i] = s * in[i]   — `zero += (f2_u, f3)` at mod.rs:71-75
+__global__ void __launch_bounds__(128) scale_kernel(const uint32_t* in, const uint32_t* s, unsigned long long n, uint32_t* out) {
+    Fr sc = fr::load(s);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        fr::store(out + i * 8, fr::mul(sc, fr::load(in + i * 8)));
+}
+
+// out = t[0] + r * (t[1] - t[0]): last fold of a 2-entry table = DenseMLE::evaluate's final step (mod.rs:122)
+__global__ void fold_pair_kernel(const uint32_t* t, const uint32_t* r, uint32_t* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        Fr a = fr::load(t), b = fr::load(t + 8), rr = fr::load(r);
+        fr::store(out, fr::add(a, fr::mul(rr, fr::sub(b, a))));
+    }
+}
+
+// Montgomery -> canonical integers (what ark-serialize emits), n elements
+__global__ void __launch_bounds__(128) to_canonical_kernel(const uint32_t* in, unsigned long long n, uint32_t* out) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        Fr one_int = fr::zero();
+        one_int.l[0] = 1;
+        fr::store(out + i * 8, fr::mul(fr::load(in + i * 8), one_int));
+    }
+}
+
+// ---- merged sparse output for the stand-alone initialize_phase_one API: after sorting (key, position) by key,
+// flag segment heads, and let one thread per head sum its segment.
+__global__ void __launch_bounds__(128) seg_heads_kernel(const unsigned long long* keys, unsigned long long n, uint32_t* head) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(128) seg_sum_kernel(const unsigned long long* keys, const uint32_t* pos, const uint32_t* head,
+                                                     const uint32_t* head_scan /* exclusive */, unsigned long long n,
+                                                     const uint32_t* w, unsigned long long* keys_out, uint32_t* vals_out) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        if (!head[i]) continue;
+        Fr acc = fr::load(w + (unsigned long long)pos[i] * 8);
+        for (unsigned long long j = i + 1; j < n && !head[j]; j++) acc = fr::add(acc, fr::load(w + (unsigned long long)pos[j] * 8));
+        keys_out[head_scan[i]] = keys[i];
+        fr::store(vals_out + (unsigned long long)head_scan[i] * 8, acc);
+    }
+}
+
+}  // namespace sck

@@ -1,0 +1,188 @@
+// Round kernels of the sumcheck prover hot path.
+//
+// round_kernel<NPTS, FOLD> is ONE launch per protocol round and fuses the two steps of
+// IPForMLSumcheck::prove_round (/root/reference/src/ml_sumcheck/protocol/prover.rs:74-153):
+//   (a2) the fix_variables fold of every table on the previous challenge r (prover.rs:85-89 -> ark-poly
+//        DenseMultilinearExtension::fix_variables: new[b] = old[2b] + r*(old[2b+1]-old[2b])), and
+//   (a1) the (d+1)-point multiply-reduce over the folded tables (prover.rs:110-148).
+// A thread that owns output pair-index b reads old[4b..4b+3] of each table (128 contiguous bytes), folds them to
+// new[2b], new[2b+1] in registers, stores those 64 bytes, and feeds them straight into the product terms, so every
+// table element is read from HBM exactly once per round and written once (SURVEY.md §8d "algorithmic bytes").
+//
+// Exactness: field arithmetic is exact and values are kept fully reduced, so factoring the coefficient out of a
+// single product and summing in a different order give the same limbs the reference produces.
+#pragma once
+#include <cstdint>
+
+#include "fr.cuh"
+
+namespace sck {
+
+using fr::Fr;
+
+constexpr int MAX_NPTS = 5;  // evaluation points handled by one launch; d+1 > 5 is split into several launches
+
+struct RoundParams {
+    const uint32_t* const* tab_in;  // [T] current tables (device pointers), length 4*n_pairs (FOLD) or 2*n_pairs
+    uint32_t* const* tab_out;       // [T] folded tables (FOLD), length 2*n_pairs
+    const uint32_t* prod_offsets;   // CSR of ProverState.list_of_products (prover.rs:24)
+    const uint32_t* prod_indices;
+    const uint8_t* prod_first;      // 1 where a CSR entry is the first use of its table (that use stores the fold)
+    const uint32_t* coeffs;         // [n_products][8]
+    uint32_t n_products;
+    uint32_t defer_coeff;           // single product: multiply the sums by coeffs[0] once at the end
+    uint32_t t0;                    // first evaluation point of this launch
+    uint32_t write_fold;            // store folded tables (only the t0 == 0 launch of a round does)
+    unsigned long long n_pairs;     // 2^(nv - round)
+    uint32_t r[8];                  // challenge of the previous round (FOLD)
+    uint32_t* partials;             // [gridDim.x][NPTS][8] scratch
+    unsigned int* counter;          // last-block election
+    uint32_t* evals_out;            // [(d+1)][8] Montgomery — ProverMsg.evaluations
+    uint32_t* canon_out;            // [(d+1)][8] canonical integers (what ark-serialize writes to the transcript)
+};
+
+// ---- block-wide sum of NPTS field elements per thread; result valid in thread 0 ------------------------------
+__device__ __forceinline__ Fr shfl_down(const Fr& v, int delta) {
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = __shfl_down_sync(0xffffffffu, v.l[i], delta);
+    return r;
+}
+
+template <int NPTS>
+__device__ __forceinline__ void block_reduce(Fr (&acc)[NPTS], uint32_t* smem /* [32][NPTS][8] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int t = 0; t < NPTS; t++) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) acc[t] = fr::add(acc[t], shfl_down(acc[t], d));
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < NPTS; t++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) smem[(warp * NPTS + t) * 8 + i] = acc[t].l[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int t = 0; t < NPTS; t++) {
+            Fr v = fr::zero();
+            if (lane < nwarps) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) v.l[i] = smem[(lane * NPTS + t) * 8 + i];
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) v = fr::add(v, shfl_down(v, d));
+            acc[t] = v;
+        }
+    }
+    __syncthreads();
+}
+
+// canonical integer of a Montgomery element: a * 1 * R^-1
+__device__ __forceinline__ Fr to_canonical(const Fr& a) {
+    Fr one_int = fr::zero();
+    one_int.l[0] = 1;
+    return fr::mul(a, one_int);
+}
+
+template <int NPTS, bool FOLD>
+__global__ void __launch_bounds__(128) round_kernel(const RoundParams p) {
+    __shared__ uint32_t s_red[32 * NPTS * 8];
+    __shared__ bool s_last;
+
+    Fr acc[NPTS];
+#pragma unroll
+    for (int t = 0; t < NPTS; t++) acc[t] = fr::zero();
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = p.r[i];
+
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < p.n_pairs; b += stride) {
+        for (uint32_t k = 0; k < p.n_products; k++) {
+            Fr prod[NPTS];
+            const uint32_t j0 = p.prod_offsets[k], j1 = p.prod_offsets[k + 1];
+            for (uint32_t jj = j0; jj < j1; jj++) {
+                const uint32_t idx = p.prod_indices[jj];
+                const uint32_t* tin = p.tab_in[idx];
+                Fr v0, v1;
+                if (FOLD) {
+                    const uint32_t* src = tin + b * 32;  // 4 elements x 8 words
+                    Fr e0 = fr::load_stream(src), e1 = fr::load_stream(src + 8), e2 = fr::load_stream(src + 16),
+                       e3 = fr::load_stream(src + 24);
+                    v0 = fr::add(e0, fr::mul(r, fr::sub(e1, e0)));
+                    v1 = fr::add(e2, fr::mul(r, fr::sub(e3, e2)));
+                    if (p.write_fold && p.prod_first[jj]) {
+                        uint32_t* dst = p.tab_out[idx] + b * 16;
+                        fr::store(dst, v0);
+                        fr::store(dst + 8, v1);
+                    }
+                } else {
+                    const uint32_t* src = tin + b * 16;
+                    v0 = fr::load_stream(src);
+                    v1 = fr::load_stream(src + 8);
+                }
+                // prover.rs:119-124: start = table[2b], step = table[2b+1] - start; product[t] *= start; start += step
+                Fr step = fr::sub(v1, v0);
+                Fr cur = v0;
+                for (uint32_t s = 0; s < p.t0; s++) cur = fr::add(cur, step);  // only for d+1 > MAX_NPTS
+                if (jj == j0) {
+                    if (!p.defer_coeff) {  // c_k * prod_j(...): scale the first multiplicand's line once
+                        Fr c = fr::load(p.coeffs + 8 * k);
+                        cur = fr::mul(cur, c);
+                        step = fr::mul(step, c);
+                    }
+#pragma unroll
+                    for (int t = 0; t < NPTS; t++) {
+                        prod[t] = cur;
+                        if (t + 1 < NPTS) cur = fr::add(cur, step);
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < NPTS; t++) {
+                        prod[t] = fr::mul(prod[t], cur);
+                        if (t + 1 < NPTS) cur = fr::add(cur, step);
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < NPTS; t++) acc[t] = fr::add(acc[t], prod[t]);  // prover.rs:126-128
+        }
+    }
+
+    block_reduce<NPTS>(acc, s_red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int t = 0; t < NPTS; t++) fr::store(p.partials + ((size_t)blockIdx.x * NPTS + t) * 8, acc[t]);
+        __threadfence();
+        unsigned int ticket = atomicAdd(p.counter, 1u);
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+
+    // Last block to finish: sum the per-block partials (prover.rs:138-148, the rayon reduce), apply the deferred
+    // coefficient, publish P(t0..t0+NPTS-1).
+    __threadfence();
+#pragma unroll
+    for (int t = 0; t < NPTS; t++) acc[t] = fr::zero();
+    for (uint32_t g = threadIdx.x; g < gridDim.x; g += blockDim.x) {
+#pragma unroll
+        for (int t = 0; t < NPTS; t++) acc[t] = fr::add(acc[t], fr::load(p.partials + ((size_t)g * NPTS + t) * 8));
+    }
+    block_reduce<NPTS>(acc, s_red);
+    if (threadIdx.x == 0) {
+        Fr c = fr::load(p.coeffs);
+#pragma unroll
+        for (int t = 0; t < NPTS; t++) {
+            Fr v = p.defer_coeff ? fr::mul(acc[t], c) : acc[t];
+            fr::store(p.evals_out + (size_t)(p.t0 + t) * 8, v);
+            fr::store(p.canon_out + (size_t)(p.t0 + t) * 8, to_canonical(v));
+        }
+        *p.counter = 0;
+    }
+}
+
+}  // namespace sck

@@ -1,0 +1,434 @@
+// libsumcheck_b200.so — C ABI (include/sumcheck_b200.h) over the sm_100a kernels in kernels.cuh.
+// Host logic here is only what the reference's L3 drivers do around the hot path: the prove_round state machine
+// (prover.rs:74-98), the round loop + Fiat-Shamir transcript (ml_sumcheck/mod.rs:50-70), buffer rotation.  All field
+// arithmetic runs on the device; there is no CPU fallback — without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sumcheck_b200.h"
+#include "blake2b.cuh"
+#include "kernels.cuh"
+#include "gkr_kernels.cuh"
+
+static_assert(sizeof(sc_blake2b512_rng) == sizeof(b2::State), "sc_blake2b512_rng must be layout-identical to b2::State");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) return fail(SC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+struct DeviceInfo {
+    bool ready = false;
+    int sms = 0;
+};
+DeviceInfo g_dev[64];
+
+int ensure_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(SC_ERR_NO_DEVICE, "no CUDA device (%s); sumcheck_b200 has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= n || device >= 64) return fail(SC_ERR_BAD_INPUT, "device %d out of range (%d visible)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    if (!g_dev[device].ready) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) return fail(SC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        CUDA_TRY(fr::fr_init_constants());
+        g_dev[device].sms = prop.multiProcessorCount;
+        g_dev[device].ready = true;
+    }
+    return SC_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ prover handle
+struct sc_prover {
+    int device = 0;
+    uint32_t nv = 0, T = 0, n_products = 0, d = 0, round = 0;
+    uint64_t N = 0;
+    bool owns_tab0 = true;
+    std::vector<uint64_t> randomness;  // ProverState.randomness, 4 u64 each
+    std::vector<uint32_t*> tab0, bufA, bufB;  // per-table device pointers
+    uint32_t *slab0 = nullptr, *slabA = nullptr, *slabB = nullptr;
+    uint32_t** d_ptr0 = nullptr;  // device arrays of table pointers
+    uint32_t** d_ptrA = nullptr;
+    uint32_t** d_ptrB = nullptr;
+    uint32_t *d_offsets = nullptr, *d_indices = nullptr, *d_coeffs = nullptr;
+    uint8_t* d_first = nullptr;
+    uint32_t *d_partials = nullptr, *d_evals = nullptr, *d_canon = nullptr;
+    unsigned int* d_counter = nullptr;
+    uint32_t *h_evals = nullptr, *h_canon = nullptr;  // pinned
+    int max_grid = 0;
+    int cur = 0;  // which buffer holds the current tables: 0 = tab0, 1 = A, 2 = B
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> ev;  // 2 per round
+    std::vector<float> round_ms;
+    bool timing = false;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+template <int NPTS, bool FOLD>
+int occupancy_blocks() {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sck::round_kernel<NPTS, FOLD>, 128, 0);
+    return nb < 1 ? 1 : nb;
+}
+
+template <int NPTS>
+cudaError_t launch_round(sc_prover* p, bool fold, const sck::RoundParams& rp) {
+    const int threads = 128;
+    unsigned long long need = (rp.n_pairs + threads - 1) / threads;
+    int occ = fold ? occupancy_blocks<NPTS, true>() : occupancy_blocks<NPTS, false>();
+    unsigned long long cap = (unsigned long long)g_dev[p->device].sms * occ;
+    if (cap > (unsigned long long)p->max_grid) cap = p->max_grid;
+    int grid = (int)(need < cap ? need : cap);
+    if (grid < 1) grid = 1;
+    if (fold)
+        sck::round_kernel<NPTS, true><<<grid, threads, 0, p->stream>>>(rp);
+    else
+        sck::round_kernel<NPTS, false><<<grid, threads, 0, p->stream>>>(rp);
+    p->launches++;
+    return cudaGetLastError();
+}
+
+// One protocol round on the device: (fold on r) + sums for all d+1 points.  Results land in d_evals / d_canon.
+int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
+    const uint32_t i = p->round;  // already incremented: 1-based round being computed
+    const bool fold = (i >= 2);
+    sck::RoundParams rp;
+    memset(&rp, 0, sizeof(rp));
+    uint32_t** in = p->cur == 0 ? p->d_ptr0 : (p->cur == 1 ? p->d_ptrA : p->d_ptrB);
+    int next = p->cur;
+    if (fold) next = (p->cur == 1) ? 2 : 1;
+    uint32_t** out = next == 1 ? p->d_ptrA : p->d_ptrB;
+    rp.tab_in = (const uint32_t* const*)in;
+    rp.tab_out = out;
+    rp.prod_offsets = p->d_offsets;
+    rp.prod_indices = p->d_indices;
+    rp.prod_first = p->d_first;
+    rp.coeffs = p->d_coeffs;
+    rp.n_products = p->n_products;
+    rp.defer_coeff = (p->n_products == 1) ? 1u : 0u;
+    rp.n_pairs = (unsigned long long)1 << (p->nv - i);
+    if (fold) memcpy(rp.r, r, 32);
+    rp.partials = p->d_partials;
+    rp.counter = p->d_counter;
+    rp.evals_out = p->d_evals;
+    rp.canon_out = p->d_canon;
+    uint32_t remaining = p->d + 1, t0 = 0;
+    while (remaining > 0) {
+        uint32_t take;
+        if (remaining <= (uint32_t)sck::MAX_NPTS) take = remaining;
+        else if (remaining == (uint32_t)sck::MAX_NPTS + 1) take = 3;
+        else take = sck::MAX_NPTS;
+        rp.t0 = t0;
+        rp.write_fold = (t0 == 0) ? 1u : 0u;
+        cudaError_t e;
+        switch (take) {
+            case 1: e = launch_round<1>(p, fold, rp); break;
+            case 2: e = launch_round<2>(p, fold, rp); break;
+            case 3: e = launch_round<3>(p, fold, rp); break;
+            case 4: e = launch_round<4>(p, fold, rp); break;
+            default: e = launch_round<5>(p, fold, rp); break;
+        }
+        if (e != cudaSuccess) return fail(SC_ERR_CUDA, "round kernel launch: %s", cudaGetErrorString(e));
+        t0 += take;
+        remaining -= take;
+    }
+    p->cur = next;
+    return SC_OK;
+}
+
+int validate_products(uint32_t n_tables, uint32_t n_products, const uint32_t* offsets, const uint32_t* indices, uint32_t* d_out) {
+    if (n_products == 0 || n_tables == 0) return fail(SC_ERR_BAD_INPUT, "empty polynomial");
+    uint32_t d = 0;
+    for (uint32_t k = 0; k < n_products; k++) {
+        if (offsets[k + 1] <= offsets[k]) return fail(SC_ERR_BAD_INPUT, "product %u is empty (data_structures.rs:78)", k);
+        uint32_t m = offsets[k + 1] - offsets[k];
+        if (m > d) d = m;
+        for (uint32_t j = offsets[k]; j < offsets[k + 1]; j++)
+            if (indices[j] >= n_tables) return fail(SC_ERR_BAD_INPUT, "table index %u out of range", indices[j]);
+    }
+    *d_out = d;
+    return SC_OK;
+}
+
+int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* const* tables, bool tables_on_device,
+                  uint32_t n_products, const uint64_t* coeffs, const uint32_t* offsets, const uint32_t* indices, int device) {
+    *out = nullptr;
+    if (nv == 0) return fail(SC_ERR_PANIC_CONSTANT, "Attempt to prove a constant.");
+    if (nv > 40) return fail(SC_ERR_BAD_INPUT, "nv = %u too large", nv);
+    uint32_t d = 0;
+    int rc = validate_products(T, n_products, offsets, indices, &d);
+    if (rc) return rc;
+    rc = ensure_device(device);
+    if (rc) return rc;
+    sc_prover* p = new sc_prover();
+    p->device = device; p->nv = nv; p->T = T; p->n_products = n_products; p->d = d; p->N = (uint64_t)1 << nv;
+    auto bail = [&](int code) { sc_prover_destroy(p); return code; };
+#define TRY_P(expr)                                                                                        \
+    do {                                                                                                   \
+        cudaError_t e__ = (expr);                                                                          \
+        if (e__ != cudaSuccess) return bail(fail(SC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__))); \
+    } while (0)
+    TRY_P(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    const size_t elem = 32, N = p->N;
+    const size_t nA = N / 2 ? N / 2 : 1, nB = N / 4 ? N / 4 : 1;
+    p->tab0.resize(T); p->bufA.resize(T); p->bufB.resize(T);
+    if (tables_on_device) {
+        p->owns_tab0 = false;
+        for (uint32_t j = 0; j < T; j++) p->tab0[j] = (uint32_t*)tables[j];
+    } else {
+        TRY_P(cudaMalloc(&p->slab0, (size_t)T * N * elem));
+        for (uint32_t j = 0; j < T; j++) {
+            p->tab0[j] = p->slab0 + (size_t)j * N * 8;
+            // deep copy of the caller's table (prover.rs:55-59); pageable or pinned source both work
+            TRY_P(cudaMemcpyAsync(p->tab0[j], tables[j], N * elem, cudaMemcpyHostToDevice, p->stream));
+        }
+    }
+    TRY_P(cudaMalloc(&p->slabA, (size_t)T * nA * elem));
+    TRY_P(cudaMalloc(&p->slabB, (size_t)T * nB * elem));
+    for (uint32_t j = 0; j < T; j++) {
+        p->bufA[j] = p->slabA + (size_t)j * nA * 8;
+        p->bufB[j] = p->slabB + (size_t)j * nB * 8;
+    }
+    TRY_P(cudaMalloc(&p->d_ptr0, T * sizeof(uint32_t*)));
+    TRY_P(cudaMalloc(&p->d_ptrA, T * sizeof(uint32_t*)));
+    TRY_P(cudaMalloc(&p->d_ptrB, T * sizeof(uint32_t*)));
+    TRY_P(cudaMemcpyAsync(p->d_ptr0, p->tab0.data(), T * sizeof(uint32_t*), cudaMemcpyHostToDevice, p->stream));
+    TRY_P(cudaMemcpyAsync(p->d_ptrA, p->bufA.data(), T * sizeof(uint32_t*), cudaMemcpyHostToDevice, p->stream));
+    TRY_P(cudaMemcpyAsync(p->d_ptrB, p->bufB.data(), T * sizeof(uint32_t*), cudaMemcpyHostToDevice, p->stream));
+    const uint32_t nnz = offsets[n_products];
+    std::vector<uint8_t> first(nnz, 0);
+    {
+        std::vector<uint8_t> seen(T, 0);
+        for (uint32_t j = 0; j < nnz; j++)
+            if (!seen[indices[j]]) { seen[indices[j]] = 1; first[j] = 1; }
+    }
+    TRY_P(cudaMalloc(&p->d_offsets, (n_products + 1) * sizeof(uint32_t)));
+    TRY_P(cudaMalloc(&p->d_indices, nnz * sizeof(uint32_t)));
+    TRY_P(cudaMalloc(&p->d_first, nnz));
+    TRY_P(cudaMalloc(&p->d_coeffs, (size_t)n_products * 32));
+    TRY_P(cudaMemcpyAsync(p->d_offsets, offsets, (n_products + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
+    TRY_P(cudaMemcpyAsync(p->d_indices, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
+    TRY_P(cudaMemcpyAsync(p->d_first, first.data(), nnz, cudaMemcpyHostToDevice, p->stream));
+    TRY_P(cudaMemcpyAsync(p->d_coeffs, coeffs, (size_t)n_products * 32, cudaMemcpyHostToDevice, p->stream));
+    p->max_grid = g_dev[device].sms * 16;
+    TRY_P(cudaMalloc(&p->d_partials, (size_t)p->max_grid * sck::MAX_NPTS * 32));
+    TRY_P(cudaMalloc(&p->d_counter, sizeof(unsigned int)));
+    TRY_P(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned int), p->stream));
+    TRY_P(cudaMalloc(&p->d_evals, (size_t)(d + 1) * 32));
+    TRY_P(cudaMalloc(&p->d_canon, (size_t)(d + 1) * 32));
+    TRY_P(cudaMallocHost(&p->h_evals, (size_t)(d + 1) * 32));
+    TRY_P(cudaMallocHost(&p->h_canon, (size_t)(d + 1) * 32));
+    p->ev.resize(2 * (size_t)nv);
+    for (auto& e : p->ev) TRY_P(cudaEventCreate(&e));
+    p->round_ms.assign(nv, 0.f);
+    p->randomness.reserve((size_t)nv * 4);
+    TRY_P(cudaStreamSynchronize(p->stream));  // uploads done: the caller may free/modify its buffers
+#undef TRY_P
+    *out = p;
+    return SC_OK;
+}
+
+// prove_round state machine (prover.rs:78-98) + device round + D2H of the d+1 results into the pinned buffers.
+int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
+    if (r_or_null) {
+        if (p->round == 0) return fail(SC_ERR_PANIC_FIRST_ROUND_MSG, "first round should be prover first.");
+        p->randomness.insert(p->randomness.end(), r_or_null, r_or_null + 4);
+    } else if (p->round > 0) {
+        return fail(SC_ERR_PANIC_MISSING_MSG, "verifier message is empty");
+    }
+    p->round += 1;
+    if (p->round > p->nv) return fail(SC_ERR_PANIC_NOT_ACTIVE, "Prover is not active");
+    CUDA_TRY(cudaSetDevice(p->device));
+    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1)], p->stream));
+    // prover.rs:85-86: r = randomness[round-1] — the challenge just pushed
+    int rc = run_round_device(p, r_or_null);
+    if (rc) return rc;
+    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));
+    const size_t bytes = (size_t)(p->d + 1) * 32;
+    CUDA_TRY(cudaMemcpyAsync(p->h_evals, p->d_evals, bytes, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->h_canon, p->d_canon, bytes, cudaMemcpyDeviceToHost, p->stream));
+    if (sync_out) CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return SC_OK;
+}
+
+// The round loop shared by MLSumcheck (mod.rs:59-64) and the two GKR phases (gkr mod.rs:111-119, 126-133):
+// prove_round -> rng.feed(&prover_msg) -> sample_round.  challenges_out: nv*4 u64.
+int run_rounds(sc_prover* p, b2::State* st, uint64_t* evals_out, uint64_t* challenges_out) {
+    const uint32_t nv = p->nv, d = p->d;
+    std::vector<uint8_t> msg(8 + 32 * (size_t)(d + 1));
+    b2::put_u64(msg.data(), d + 1);
+    uint64_t r[4];
+    bool have_r = false;
+    p->timing = true;
+    for (uint32_t i = 0; i < nv; i++) {
+        int rc = prove_round_impl(p, have_r ? r : nullptr, true);
+        if (rc) { p->timing = false; return rc; }
+        memcpy(evals_out + (size_t)i * (d + 1) * 4, p->h_evals, (size_t)(d + 1) * 32);
+        memcpy(msg.data() + 8, p->h_canon, (size_t)(d + 1) * 32);
+        b2::update(st, msg.data(), msg.size());
+        b2::sample_fr(st, r);
+        have_r = true;
+        memcpy(challenges_out + (size_t)i * 4, r, 32);
+    }
+    p->timing = false;
+    for (uint32_t i = 0; i < nv; i++) cudaEventElapsedTime(&p->round_ms[i], p->ev[2 * i], p->ev[2 * i + 1]);
+    return SC_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* sc_last_error(void) { return g_err.c_str(); }
+
+int sc_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(SC_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+void sc_rng_setup(sc_blake2b512_rng* rng) { b2::init((b2::State*)rng); }
+void sc_rng_feed_bytes(sc_blake2b512_rng* rng, const uint8_t* b, size_t n) { b2::update((b2::State*)rng, b, n); }
+void sc_rng_fill_bytes(sc_blake2b512_rng* rng, uint8_t* dest, size_t n) { b2::fill_bytes((b2::State*)rng, dest, n); }
+uint64_t sc_rng_next_u64(sc_blake2b512_rng* rng) { return b2::next_u64((b2::State*)rng); }
+void sc_rng_sample_fr(sc_blake2b512_rng* rng, uint64_t out[4]) { b2::sample_fr((b2::State*)rng, out); }
+
+int sc_prover_create(sc_prover** out, uint32_t nv, uint32_t n_tables, const uint64_t* const* tables, uint32_t n_products,
+                     const uint64_t* coeffs, const uint32_t* offsets, const uint32_t* indices, int device) {
+    return create_common(out, nv, n_tables, tables, false, n_products, coeffs, offsets, indices, device);
+}
+int sc_prover_create_device(sc_prover** out, uint32_t nv, uint32_t n_tables, const uint64_t* const* d_tables,
+                            uint32_t n_products, const uint64_t* coeffs, const uint32_t* offsets, const uint32_t* indices,
+                            int device) {
+    return create_common(out, nv, n_tables, d_tables, true, n_products, coeffs, offsets, indices, device);
+}
+
+void sc_prover_destroy(sc_prover* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->owns_tab0) cudaFree(p->slab0);
+    cudaFree(p->slabA); cudaFree(p->slabB);
+    cudaFree(p->d_ptr0); cudaFree(p->d_ptrA); cudaFree(p->d_ptrB);
+    cudaFree(p->d_offsets); cudaFree(p->d_indices); cudaFree(p->d_first); cudaFree(p->d_coeffs);
+    cudaFree(p->d_partials); cudaFree(p->d_counter); cudaFree(p->d_evals); cudaFree(p->d_canon);
+    if (p->h_evals) cudaFreeHost(p->h_evals);
+    if (p->h_canon) cudaFreeHost(p->h_canon);
+    for (auto e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int sc_prover_reset(sc_prover* p) {
+    p->round = 0;
+    p->cur = 0;
+    p->randomness.clear();
+    p->launches = 0;
+    return SC_OK;
+}
+
+int sc_prove_round(sc_prover* p, const uint64_t* r_or_null, uint64_t* evals_out) {
+    int rc = prove_round_impl(p, r_or_null, true);
+    if (rc) return rc;
+    memcpy(evals_out, p->h_evals, (size_t)(p->d + 1) * 32);
+    return SC_OK;
+}
+
+uint32_t sc_prover_max_multiplicands(const sc_prover* p) { return p->d; }
+uint32_t sc_prover_num_vars(const sc_prover* p) { return p->nv; }
+uint32_t sc_prover_round(const sc_prover* p) { return p->round; }
+uint32_t sc_prover_randomness(const sc_prover* p, uint64_t* out, uint32_t cap) {
+    uint32_t n = (uint32_t)(p->randomness.size() / 4);
+    uint32_t c = n < cap ? n : cap;
+    if (out && c) memcpy(out, p->randomness.data(), (size_t)c * 32);
+    return n;
+}
+
+int sc_prover_push_randomness(sc_prover* p, const uint64_t r[4]) {
+    p->randomness.insert(p->randomness.end(), r, r + 4);
+    return SC_OK;
+}
+
+int sc_prover_table(const sc_prover* p, uint32_t j, uint64_t* out, uint64_t cap_elems, uint64_t* len_out) {
+    if (j >= p->T) return fail(SC_ERR_BAD_INPUT, "table %u out of range", j);
+    // after round i >= 2 the tables have been folded i-1 times
+    uint64_t len = p->round <= 1 ? p->N : (p->N >> (p->round - 1));
+    if (len_out) *len_out = len;
+    if (!out) return SC_OK;
+    if (cap_elems < len) return fail(SC_ERR_BAD_INPUT, "buffer too small: %llu < %llu", (unsigned long long)cap_elems, (unsigned long long)len);
+    const uint32_t* src = p->cur == 0 ? p->tab0[j] : (p->cur == 1 ? p->bufA[j] : p->bufB[j]);
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaMemcpyAsync(out, src, len * 32, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return SC_OK;
+}
+
+int sc_ml_prove(sc_prover* p, sc_blake2b512_rng* rng, uint64_t* evals_out, uint64_t* randomness_out) {
+    if (p->round != 0) return fail(SC_ERR_BAD_INPUT, "sc_ml_prove needs a prover at round 0 (got %u)", p->round);
+    b2::State* st = (b2::State*)rng;
+    uint8_t info[16];
+    b2::put_u64(info, p->d);       // PolynomialInfo.max_multiplicands  (data_structures.rs:50-55)
+    b2::put_u64(info + 8, p->nv);  // PolynomialInfo.num_variables
+    b2::update(st, info, 16);      // mod.rs:54 fs_rng.feed(&polynomial.info())
+    std::vector<uint64_t> ch((size_t)p->nv * 4);
+    int rc = run_rounds(p, st, evals_out, ch.data());  // mod.rs:59-64
+    if (rc) return rc;
+    p->randomness.insert(p->randomness.end(), ch.end() - 4, ch.end());  // mod.rs:65-67
+    if (randomness_out) memcpy(randomness_out, p->randomness.data(), (size_t)p->nv * 32);
+    return SC_OK;
+}
+
+int sc_ml_prove_oneshot(uint32_t nv, uint32_t n_tables, const uint64_t* const* tables, uint32_t n_products,
+                        const uint64_t* coeffs, const uint32_t* offsets, const uint32_t* indices, int device,
+                        uint64_t* evals_out, uint64_t* randomness_out) {
+    sc_prover* p = nullptr;
+    int rc = sc_prover_create(&p, nv, n_tables, tables, n_products, coeffs, offsets, indices, device);
+    if (rc) return rc;
+    sc_blake2b512_rng rng;
+    sc_rng_setup(&rng);  // mod.rs:43
+    rc = sc_ml_prove(p, &rng, evals_out, randomness_out);
+    sc_prover_destroy(p);
+    return rc;
+}
+
+size_t sc_serialize_proof(const uint64_t* evals, uint32_t nv, uint32_t d, uint8_t* out);  // defined in gkr/serialize section
+
+uint32_t sc_prover_round_times_ms(const sc_prover* p, float* out, uint32_t cap) {
+    uint32_t c = p->nv < cap ? p->nv : cap;
+    if (out && c) memcpy(out, p->round_ms.data(), c * sizeof(float));
+    return p->nv;
+}
+uint64_t sc_prover_launch_count(const sc_prover* p) { return p->launches; }
+
+}  // extern "C"
+
+#include "capi_gkr.inc"

@@ -1,0 +1,304 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (sumcheck_b200 -> libsumcheck_b200.so), against
+the CPU oracle on identical inputs, against the committed golden fixtures, and at BASELINE.json's full sizes.
+Bar: bit-exact (integer field arithmetic) — every comparison is exact equality of limbs / bytes."""
+import glob
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import sumcheck_b200 as sc
+from oracle import pymodel as pm
+from helpers import gkr_arrays, limbs, random_gkr, random_instance, table_limbs
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.json")))
+
+
+def h2i(x):
+    return int(x, 16)
+
+
+def build_poly(nv, tables, products):
+    """tables: list of [2^nv,4] arrays; products: [(coeff[4], [idx])] -> (product ListOfProducts, same for the oracle)."""
+    poly = sc.ListOfProductsOfPolynomials.new(nv)
+    for c, ix in products:
+        poly.add_product([tables[j] for j in ix], c)
+    return poly
+
+
+def both_polys(orc, nv, tables_int, products_int):
+    tabs = [table_limbs(t) for t in tables_int]
+    prods = [(limbs(c), ix) for c, ix in products_int]
+    opoly = orc.Poly(nv, tabs, prods)
+    return build_poly(nv, opoly.tables, prods), opoly
+
+
+def assert_same_proof(orc, poly, opoly, pre_feed=b""):
+    rng, orng = sc.Blake2b512Rng.setup(), orc.Rng()
+    if pre_feed:
+        rng.feed(pre_feed)
+        orng.feed_bytes(pre_feed)
+    proof, state = sc.MLSumcheck.prove_as_subprotocol(rng, poly)
+    evals, rand, fin = orc.ml_prove(opoly, orng)
+    got = np.stack([m.evaluations for m in proof])
+    assert np.array_equal(got, evals)
+    assert sc.MLSumcheck.serialize_proof(proof) == orc.serialize_proof(evals)
+    assert np.array_equal(state.randomness, rand)                      # ProverState.randomness (test.rs:119)
+    # the 2-entry tables left in ProverState; the product flattens tables in first-use order (data_structures.rs:84-92)
+    order = [next(k for k, t in enumerate(opoly.tables) if t is ft) for ft in poly.flattened_ml_extensions]
+    for j, t in enumerate(state.flattened_ml_extensions):
+        assert np.array_equal(t, fin[order[j]])
+    # the transcripts stay in lock-step afterwards
+    assert rng.next_u64() == orng.next_u64()
+    return got, rand
+
+
+def test_device_is_b200_class():
+    import torch
+    assert torch.cuda.is_available()
+    assert sc.lib().sc_device_count() >= 1
+    assert torch.cuda.get_device_capability(0)[0] >= 10
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if json.load(open(p))["kind"] == "ml"], ids=os.path.basename)
+def test_ml_golden(orc, path):
+    c = json.load(open(path))
+    tables = [table_limbs([h2i(v) for v in t]) for t in c["tables"]]
+    poly = build_poly(c["nv"], tables, [(limbs(h2i(cf)), ix) for cf, ix in c["products"]])
+    rng = sc.Blake2b512Rng.setup()
+    if c["pre_feed"]:
+        rng.feed(bytes.fromhex(c["pre_feed"]))
+    proof, state = sc.MLSumcheck.prove_as_subprotocol(rng, poly)
+    assert sc.MLSumcheck.serialize_proof(proof).hex() == c["proof_bytes"]
+    assert [pm.from_mont_limbs(r) for r in state.randomness] == [h2i(r) for r in c["randomness"]]
+    assert pm.from_mont_limbs(sc.MLSumcheck.extract_sum(proof)) == h2i(c["sum"])
+
+
+@pytest.mark.parametrize("path", [p for p in GOLDEN if json.load(open(p))["kind"] == "gkr"], ids=os.path.basename)
+def test_gkr_golden(path):
+    c = json.load(open(path))
+    dim = c["dim"]
+    f1 = sc.SparseMultilinearExtension(3 * dim, np.array([h2i(i) for i, _ in c["f1"]], dtype=np.uint64),
+                                       table_limbs([h2i(v) for _, v in c["f1"]]))
+    f2, f3, g = (table_limbs([h2i(x) for x in c[k]]) for k in ("f2", "f3", "g"))
+    proof, u, v = sc.GKRRoundSumcheck.prove(sc.Blake2b512Rng.setup(), f1, f2, f3, g, return_challenges=True)
+    to_int = lambda msgs: [[pm.from_mont_limbs(e) for e in m.evaluations] for m in msgs]
+    assert to_int(proof.phase1_sumcheck_msgs) == [[h2i(x) for x in m] for m in c["phase1"]]
+    assert to_int(proof.phase2_sumcheck_msgs) == [[h2i(x) for x in m] for m in c["phase2"]]
+    assert [pm.from_mont_limbs(x) for x in u] == [h2i(x) for x in c["u"]]
+    assert [pm.from_mont_limbs(x) for x in v] == [h2i(x) for x in c["v"]]
+    assert pm.from_mont_limbs(proof.extract_sum()) == h2i(c["sum"])
+
+
+@pytest.mark.parametrize("nv,n_products,mult_range,shared", [
+    (1, 5, (4, 13), False),    # test_trivial_polynomial (ml_sumcheck/test.rs:122-144): d up to 12 -> chunked eval points
+    (2, 3, (1, 4), False),
+    (3, 2, (6, 8), False),     # d+1 in {7,8}: 5+2 / 5+3 launches per round
+    (5, 1, (6, 7), False),     # d+1 = 7
+    (7, 5, (4, 9), False),     # test_normal_polynomial shape (test.rs:145-167) at a smaller nv
+    (8, 3, (3, 4), False),     # test_extract_sum shape (test.rs:206-213)
+    (8, 5, (1, 4), True),      # test_shared_reference shape (test.rs:215-269): shared tables, repeats, short products
+    (9, 1, (1, 2), False),     # a single table, d = 1
+    (12, 1, (2, 3), False),    # BASELINE config 1: nv=12, 1 product of degree 2
+    (12, 5, (4, 9), False),    # test_normal_polynomial at its real size
+])
+def test_ml_prove_matches_oracle(orc, nv, n_products, mult_range, shared):
+    tables, products = random_instance(500 + 7 * nv + n_products, nv, n_products, mult_range, shared)
+    poly, opoly = both_polys(orc, nv, tables, products)
+    assert len(poly.flattened_ml_extensions) == len(opoly.tables)      # de-duplication (test.rs:254,258)
+    got, rand = assert_same_proof(orc, poly, opoly, pre_feed=b"Test Trivial Works" if nv % 2 else b"")
+    if nv <= 9:
+        assert pm.from_mont_limbs(sc.MLSumcheck.extract_sum([sc.ProverMsg(got[0])])) == pm.true_sum(nv, tables, products)
+
+
+def test_interactive_rounds_state_machine_and_edge_challenges(orc):
+    """test_protocol (test.rs:77-97): arbitrary challenges incl. 0, 1, p-1; tables compared after every round; the
+    reference's panics (prover.rs:79-81, 90-92, 96-98)."""
+    nv = 6
+    tables, products = random_instance(77, nv, 3, (2, 5))
+    poly, opoly = both_polys(orc, nv, tables, products)
+    st, ost = sc.IPForMLSumcheck.prover_init(poly), orc.Prover(opoly)
+    with pytest.raises(sc.Panic) as e:
+        sc.IPForMLSumcheck.prove_round(sc.IPForMLSumcheck.prover_init(poly), sc.VerifierMsg(limbs(5)))
+    assert e.value.code == -2
+    rnd = random.Random(9)
+    chal = [0, 1, pm.P - 1, 2, rnd.randrange(pm.P), rnd.randrange(pm.P)]
+    v_msg = None
+    for i in range(nv):
+        m = sc.IPForMLSumcheck.prove_round(st, v_msg)
+        om = ost.prove_round(None if v_msg is None else v_msg.randomness)
+        assert np.array_equal(m.evaluations, om)
+        assert st.round == i + 1
+        for j, ft in enumerate(poly.flattened_ml_extensions):
+            k = next(k for k, t in enumerate(opoly.tables) if t is ft)
+            assert np.array_equal(st.table(j), ost.table(k))
+        v_msg = sc.VerifierMsg(limbs(chal[i]))
+    with pytest.raises(sc.Panic) as e:
+        sc.IPForMLSumcheck.prove_round(st, None)
+    assert e.value.code == -3
+    with pytest.raises(sc.Panic) as e:
+        sc.IPForMLSumcheck.prove_round(st, v_msg)
+    assert e.value.code == -4
+
+
+def test_special_values(orc):
+    """Tables made of 0, 1, p-1 and coefficient 1 / p-1 (SURVEY §8d edge set)."""
+    nv = 5
+    rnd = random.Random(3)
+    pool = [0, 1, pm.P - 1, 2, pm.P - 2]
+    tables = [[rnd.choice(pool) for _ in range(1 << nv)] for _ in range(3)]
+    products = [(1, [0, 1, 2]), (pm.P - 1, [2, 2]), (0, [1])]
+    poly, opoly = both_polys(orc, nv, tables, products)
+    assert_same_proof(orc, poly, opoly)
+
+
+def test_generic_feedable_rng_path(orc):
+    """prove_as_subprotocol with a FeedableRNG that is not the built-in one: per-round C calls, host-side loop."""
+    class Wrapped:  # same stream as Blake2b512Rng, but opaque to the library
+        def __init__(self): self.inner = sc.Blake2b512Rng.setup(); self.state = self.inner.state
+        def feed(self, b): self.inner.feed(b)
+    nv = 6
+    tables, products = random_instance(31, nv, 2, (2, 4))
+    poly, opoly = both_polys(orc, nv, tables, products)
+    proof, _ = sc.MLSumcheck.prove_as_subprotocol(Wrapped(), poly)
+    evals, _, _ = orc.ml_prove(opoly)
+    assert np.array_equal(np.stack([m.evaluations for m in proof]), evals)
+
+
+def test_reset_reproves_identically(orc):
+    nv = 10
+    tabs = [orc.synth_table(1 << nv, 900 + j) for j in range(3)]
+    prods = [(orc.synth_table(1, 77)[0], [0, 1, 2])]
+    poly = build_poly(nv, tabs, prods)
+    st = sc.IPForMLSumcheck.prover_init(poly)
+    import ctypes as C
+    outs = []
+    for _ in range(3):
+        rng = sc.Blake2b512Rng.setup()
+        ev = np.zeros((nv, 4, 4), dtype=np.uint64)
+        assert sc.lib().sc_ml_prove(st._h, C.byref(rng.state), ev.ctypes.data_as(sc.capi.U64P), None) == 0
+        outs.append(ev)
+        st.reset()
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert np.array_equal(outs[0], orc.ml_prove(orc.Poly(nv, tabs, prods))[0])
+
+
+# ------------------------------------------------------------------------------------------- BASELINE.json sizes
+def synth_poly(orc, cfg, nv, n_products, m):
+    """SURVEY §8d synthetic inputs: table j of config c uses seed 0x5C0000 + 0x100*c + j, coefficients 0x5C00FF + 0x100*c."""
+    T = n_products * m
+    tabs = [orc.synth_table(1 << nv, 0x5C0000 + 0x100 * cfg + j) for j in range(T)]
+    coeffs = orc.synth_table(n_products, 0x5C00FF + 0x100 * cfg)
+    prods = [(coeffs[k], list(range(k * m, (k + 1) * m))) for k in range(n_products)]
+    return tabs, prods
+
+
+@pytest.mark.parametrize("cfg,nv,n_products,m", [
+    (1, 12, 1, 2),   # config 1 (bit-exact check)
+    (2, 20, 1, 3),   # config 2: nv=20 deg 3
+    (4, 18, 4, 4),   # config 4 shape at nv=18 (full nv=22 below)
+])
+def test_baseline_configs_bit_exact(orc, cfg, nv, n_products, m):
+    tabs, prods = synth_poly(orc, cfg, nv, n_products, m)
+    orc.set_threads(os.cpu_count() or 1)
+    try:
+        opoly = orc.Poly(nv, tabs, prods)
+        assert_same_proof(orc, build_poly(nv, opoly.tables, prods), opoly)
+    finally:
+        orc.set_threads(1)
+
+
+@pytest.mark.parametrize("cfg,nv,n_products,m", [
+    (3, 24, 1, 3),   # config 3 per-GPU shape at G=1: nv=24 deg 3 (1.5 GiB of tables)
+    (4, 22, 4, 4),   # config 4: nv=22, 4 products of degree 4 (2 GiB of tables)
+])
+def test_full_size_configs(orc, cfg, nv, n_products, m):
+    """Full BASELINE sizes: bit-exact against the multi-threaded oracle AND the size-independent relations the
+    reference's own tests use (verify accepts; poly.evaluate(point) == expected_evaluation, test.rs:64-75)."""
+    tabs, prods = synth_poly(orc, cfg, nv, n_products, m)
+    poly, opoly = build_poly(nv, tabs, prods), orc.Poly(nv, tabs, prods)
+    proof = sc.MLSumcheck.prove(poly)
+    got = np.stack([pm_.evaluations for pm_ in proof])
+    claimed = sc.MLSumcheck.extract_sum(proof)
+    point, expected = orc.ml_verify(nv, m, claimed, got)               # oracle verifier accepts the GPU proof
+    assert np.array_equal(orc.poly_evaluate(opoly, point), expected)   # subclaim holds on the real polynomial
+    orc.set_threads(os.cpu_count() or 1)
+    try:
+        evals, _, _ = orc.ml_prove(opoly)
+    finally:
+        orc.set_threads(1)
+    assert np.array_equal(got, evals)
+
+
+# ------------------------------------------------------------------------------------------- GKR
+@pytest.mark.parametrize("dim,nnz", [(1, None), (2, 3), (3, None), (6, None), (9, None), (7, 5), (10, 3000)])
+def test_gkr_matches_oracle(orc, dim, nnz):
+    """gkr test.rs:71-88 (test_small dim=9, test_extract dim=6) + sparse/dense extremes."""
+    f1, f2, f3, g = random_gkr(60 + dim, dim, nnz)
+    idx, val, a2, a3, ag = gkr_arrays(f1, f2, f3, g)
+    f1s = sc.SparseMultilinearExtension(3 * dim, idx, val)
+    proof, u, v = sc.GKRRoundSumcheck.prove(sc.Blake2b512Rng.setup(), f1s, a2, a3, ag, return_challenges=True)
+    m1, m2, ou, ov = orc.gkr_prove(orc.Rng(), dim, idx, val, a2, a3, ag)
+    assert np.array_equal(np.stack([m.evaluations for m in proof.phase1_sumcheck_msgs]), m1)
+    assert np.array_equal(np.stack([m.evaluations for m in proof.phase2_sumcheck_msgs]), m2)
+    assert np.array_equal(u, ou) and np.array_equal(v, ov)
+    claimed = proof.extract_sum()
+    if dim <= 7:
+        assert pm.from_mont_limbs(claimed) == pm.gkr_sum_naive(f1, f2, f3, g)       # test_extract
+    vu, vv, exp = orc.gkr_verify(orc.Rng(), dim, m1, m2, claimed)                  # verify accepts
+    assert orc.gkr_verify_subclaim(dim, idx, val, a2, a3, ag, vu, vv, exp)         # verify_subclaim true
+
+
+def test_gkr_phase_initialisers(orc):
+    """initialize_phase_one / initialize_phase_two / start_phase{1,2}_sumcheck as free functions (mod.rs:22-82)."""
+    dim = 7
+    f1, f2, f3, g = random_gkr(99, dim, 300)
+    # force collisions: several nonzeros sharing (x, y) but differing in z
+    f1 = dict(f1)
+    keys = list(f1.keys())[:40]
+    for k in keys:
+        f1[(k & ~((1 << dim) - 1)) | ((k + 1) & ((1 << dim) - 1))] = f1[k]
+    idx, val, a2, a3, ag = gkr_arrays(f1, f2, f3, g)
+    f1s = sc.SparseMultilinearExtension(3 * dim, idx, val)
+    h_g, f1_g = sc.initialize_phase_one(f1s, a3, ag)
+    oh, oi, ov = orc.gkr_initialize_phase_one(dim, idx, val, a3, ag)
+    assert np.array_equal(h_g, oh)
+    assert np.array_equal(f1_g.indices, oi) and np.array_equal(f1_g.values, ov)     # merged, BTreeMap order
+    u = table_limbs([random.Random(5).randrange(pm.P) for _ in range(dim)])
+    f1_gu = sc.initialize_phase_two(f1_g, u)
+    assert np.array_equal(f1_gu, orc.gkr_initialize_phase_two(dim, oi, ov, u))
+    # start_phase1: first round message of 1*(h_g*f2)
+    st = sc.start_phase1_sumcheck(h_g, a2)
+    m = sc.IPForMLSumcheck.prove_round(st, None)
+    op = orc.Prover(orc.Poly(dim, [oh, a2], [(sc.api.FR_ONE, [0, 1])]))
+    assert np.array_equal(m.evaluations, op.prove_round())
+    # start_phase2: tables are (f1_gu, f2_u * f3)
+    f2_u = orc.dense_evaluate(a2, u)
+    st2 = sc.start_phase2_sumcheck(f1_gu, a3, f2_u)
+    scaled = np.stack([orc.fr_op("mul", f2_u, x) for x in a3])
+    assert np.array_equal(st2.table(1), scaled)
+    m2 = sc.IPForMLSumcheck.prove_round(st2, None)
+    op2 = orc.Prover(orc.Poly(dim, [f1_gu, scaled], [(sc.api.FR_ONE, [0, 1])]))
+    assert np.array_equal(m2.evaluations, op2.prove_round())
+
+
+def test_gkr_config5_dim18(orc):
+    """BASELINE config 5: GKRRoundSumcheck prove, dim=18, f1 with 2^18 nonzeros over 54 variables."""
+    dim = 18
+    n = 1 << dim
+    f2, f3 = orc.synth_table(n, 0x5C0500), orc.synth_table(n, 0x5C0501)
+    g = orc.synth_table(dim, 0x5C0502)
+    val = orc.synth_table(n, 0x5C0503)
+    rng = np.random.default_rng(0x5C0504)
+    idx = np.unique(rng.integers(0, 1 << (3 * dim), size=n + 4096, dtype=np.uint64))[:n].copy()
+    rng.shuffle(idx)
+    f1s = sc.SparseMultilinearExtension(3 * dim, idx, val[:idx.shape[0]].copy())
+    proof, u, v = sc.GKRRoundSumcheck.prove(sc.Blake2b512Rng.setup(), f1s, f2, f3, g, return_challenges=True)
+    m1, m2, ou, ov = orc.gkr_prove(orc.Rng(), dim, f1s.indices, f1s.values, f2, f3, g)
+    assert np.array_equal(np.stack([m.evaluations for m in proof.phase1_sumcheck_msgs]), m1)
+    assert np.array_equal(np.stack([m.evaluations for m in proof.phase2_sumcheck_msgs]), m2)
+    vu, vv, exp = orc.gkr_verify(orc.Rng(), dim, m1, m2, proof.extract_sum())
+    assert orc.gkr_verify_subclaim(dim, f1s.indices, f1s.values, f2, f3, g, vu, vv, exp)
