@@ -72,6 +72,13 @@ void sc_prover_destroy(sc_prover *p);
 /* Rewind to round 0 on the tables given at creation (they are kept pristine in HBM); for repeated proofs. */
 int sc_prover_reset(sc_prover *p);
 
+/* Replace the resident tables with new host data of the same shape (H2D into the pristine copies) and rewind to
+ * round 0: the per-proof upload of a caller that proves many polynomials of one shape with one handle. */
+int sc_prover_load_tables(sc_prover *p, const uint64_t *const *tables);
+/* Run this handle's kernels and copies on the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores
+ * the handle's own stream), so the caller can order / time the work with its own events. */
+int sc_prover_set_stream(sc_prover *p, void *cuda_stream);
+
 /* IPForMLSumcheck::prove_round (prover.rs:74-153).  r_or_null = Some(VerifierMsg{randomness}) / None.
  * evals_out receives ProverMsg.evaluations: (max_multiplicands+1) x 4 u64, P(0)..P(d). */
 int sc_prove_round(sc_prover *p, const uint64_t *r_or_null, uint64_t *evals_out);
@@ -101,6 +108,10 @@ int sc_ml_prove_oneshot(uint32_t nv, uint32_t n_tables, const uint64_t *const *t
 /* ark-serialize bytes of Proof<F> = Vec<ProverMsg<F>> (what `proof.serialize_uncompressed` yields): returns the
  * byte count 8 + nv*(8 + 32*(d+1)); writes when out != NULL. */
 size_t sc_serialize_proof(const uint64_t *evals, uint32_t nv, uint32_t d, uint8_t *out);
+
+/* Synthetic-input helper for benches and smoke runs (not part of the reference surface): fills `out` with n_elems
+ * uniform Fr elements (Montgomery limbs) from a counter-based SplitMix64 stream — see sumcheck_b200/synth.py. */
+void sc_synth_table(uint64_t *out, uint64_t n_elems, uint64_t seed);
 
 /* Per-round device timings of the last sc_ml_prove on this handle (ms, CUDA events on the launching stream):
  * copies min(nv, cap) values, returns nv. Kernel-only; excludes transcript/host time. */

@@ -232,6 +232,17 @@ class ProverState:
     def reset(self):
         _check(capi.lib().sc_prover_reset(self._h))
 
+    def load_tables(self, tables):
+        tabs = (C.c_void_p * len(tables))(*[t.ctypes.data for t in tables])
+        _check(capi.lib().sc_prover_load_tables(self._h, tabs))
+
+    def set_stream(self, cuda_stream):
+        _check(capi.lib().sc_prover_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def prove_into(self, rng, evals):
+        """sc_ml_prove on this (round-0) handle into a preallocated [nv, d+1, 4] array."""
+        _check(capi.lib().sc_ml_prove(self._h, C.byref(rng.state), _p64(evals), None))
+
     def round_times_ms(self):
         nv = self.num_vars
         out = np.zeros(nv, dtype=np.float32)

@@ -31,6 +31,8 @@ SIGNATURES = {
                                           U64P, U32P, U32P, C.c_int]),
     "sc_prover_destroy": (None, [C.c_void_p]),
     "sc_prover_reset": (C.c_int, [C.c_void_p]),
+    "sc_prover_load_tables": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "sc_prover_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sc_prove_round": (C.c_int, [C.c_void_p, U64P, U64P]),
     "sc_prover_max_multiplicands": (C.c_uint32, [C.c_void_p]),
     "sc_prover_num_vars": (C.c_uint32, [C.c_void_p]),
@@ -42,6 +44,7 @@ SIGNATURES = {
     "sc_ml_prove_oneshot": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, U64P, U32P, U32P, C.c_int,
                                       U64P, U64P]),
     "sc_serialize_proof": (C.c_size_t, [U64P, C.c_uint32, C.c_uint32, U8P]),
+    "sc_synth_table": (None, [U64P, C.c_uint64, C.c_uint64]),
     "sc_prover_round_times_ms": (C.c_uint32, [C.c_void_p, F32P, C.c_uint32]),
     "sc_prover_launch_count": (C.c_uint64, [C.c_void_p]),
     "sc_gkr_initialize_phase_one": (C.c_int, [C.c_uint32, C.c_uint64, U64P, U64P, U64P, U64P, C.c_int, U64P, U64P, U64P, U64P]),

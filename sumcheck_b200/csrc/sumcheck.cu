@@ -82,7 +82,8 @@ struct sc_prover {
     uint32_t *h_evals = nullptr, *h_canon = nullptr;  // pinned
     int max_grid = 0;
     int cur = 0;  // which buffer holds the current tables: 0 = tab0, 1 = A, 2 = B
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // the stream work is issued on
+    cudaStream_t own_stream = nullptr;  // created by the handle
     std::vector<cudaEvent_t> ev;  // 2 per round
     std::vector<float> round_ms;
     bool timing = false;
@@ -195,7 +196,8 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
         cudaError_t e__ = (expr);                                                                          \
         if (e__ != cudaSuccess) return bail(fail(SC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__))); \
     } while (0)
-    TRY_P(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    TRY_P(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+    p->stream = p->own_stream;
     const size_t elem = 32, N = p->N;
     const size_t nA = N / 2 ? N / 2 : 1, nB = N / 4 ? N / 4 : 1;
     p->tab0.resize(T); p->bufA.resize(T); p->bufB.resize(T);
@@ -344,7 +346,7 @@ void sc_prover_destroy(sc_prover* p) {
     if (p->h_evals) cudaFreeHost(p->h_evals);
     if (p->h_canon) cudaFreeHost(p->h_canon);
     for (auto e : p->ev) if (e) cudaEventDestroy(e);
-    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
 }
 
@@ -353,6 +355,22 @@ int sc_prover_reset(sc_prover* p) {
     p->cur = 0;
     p->randomness.clear();
     p->launches = 0;
+    return SC_OK;
+}
+
+int sc_prover_load_tables(sc_prover* p, const uint64_t* const* tables) {
+    if (!p->owns_tab0) return fail(SC_ERR_BAD_INPUT, "handle was created over caller-owned device tables");
+    CUDA_TRY(cudaSetDevice(p->device));
+    for (uint32_t j = 0; j < p->T; j++)
+        CUDA_TRY(cudaMemcpyAsync(p->tab0[j], tables[j], p->N * 32, cudaMemcpyHostToDevice, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return sc_prover_reset(p);
+}
+
+int sc_prover_set_stream(sc_prover* p, void* cuda_stream) {
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    p->stream = cuda_stream ? (cudaStream_t)cuda_stream : p->own_stream;
     return SC_OK;
 }
 
@@ -421,6 +439,31 @@ int sc_ml_prove_oneshot(uint32_t nv, uint32_t n_tables, const uint64_t* const* t
 }
 
 size_t sc_serialize_proof(const uint64_t* evals, uint32_t nv, uint32_t d, uint8_t* out);  // defined in gkr/serialize section
+
+void sc_synth_table(uint64_t* out, uint64_t n_elems, uint64_t seed) {
+    const uint64_t GAMMA = 0x9e3779b97f4a7c15ULL;
+    const uint64_t P[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
+    auto mix = [](uint64_t z) {
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        return z ^ (z >> 31);
+    };
+    for (uint64_t e = 0; e < n_elems; e++) {
+        uint64_t t[4];
+        for (uint64_t k = 0; k < 8; k++) {
+            for (uint64_t i = 0; i < 4; i++) t[i] = mix(seed + GAMMA * (((e * 8 + k) * 4) + i + 1));
+            t[3] &= 0x7fffffffffffffffULL;
+            bool lt = false;
+            for (int i = 3; i >= 0; i--) {
+                if (t[i] < P[i]) { lt = true; break; }
+                if (t[i] > P[i]) break;
+            }
+            if (lt) break;
+            if (k == 7) t[3] &= 0x3fffffffffffffffULL;
+        }
+        memcpy(out + 4 * e, t, 32);
+    }
+}
 
 uint32_t sc_prover_round_times_ms(const sc_prover* p, float* out, uint32_t cap) {
     uint32_t c = p->nv < cap ? p->nv : cap;

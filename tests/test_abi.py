@@ -68,3 +68,11 @@ def test_nv0_panics_before_touching_the_device():
     with pytest.raises(Panic) as e:   # zero_polynomial_should_error (ml_sumcheck/test.rs:187-204)
         IPForMLSumcheck.prover_init(poly)
     assert e.value.code == -1
+
+
+def test_synth_generators_agree(orc):
+    """numpy twin == C helper in the product library == the oracle's generator."""
+    from sumcheck_b200.synth import synth_table, synth_table_fast
+    for seed in (0x5C0000, 0x5C0301, 1):
+        a, b, c = synth_table(5000, seed), synth_table_fast(5000, seed), orc.synth_table(5000, seed)
+        assert np.array_equal(a, b) and np.array_equal(a, c)
