@@ -57,7 +57,8 @@ SIGNATURES = {
 
 
 def lib_path():
-    return os.path.join(_HERE, "libsumcheck_b200.so")
+    # SC_LIB selects an alternative build of the SAME library (kernel-variant experiments under tools/); never a fallback
+    return os.environ.get("SC_LIB") or os.path.join(_HERE, "libsumcheck_b200.so")
 
 
 def lib():

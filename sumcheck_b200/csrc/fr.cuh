@@ -169,6 +169,89 @@ __device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) {
     return reduce_once(t);
 }
 
+
+// ---- lazily reduced inner products -----------------------------------------------------------------------------
+// A WideAcc holds an UNREDUCED integer sum of Montgomery products x*y (each < p^2 < 2^510) in 17 limbs, so 2^34
+// products can be accumulated before overflow.  One Montgomery reduction at the end turns the whole sum into a field
+// element: sum_b x_b*y_b*R^-1 mod p — the same value as reducing every product first, because the field arithmetic is
+// exact.  This halves the IMAD.WIDE cost of the last multiply of every product term (64 instead of 112).
+struct WideAcc {
+    uint32_t l[17];
+};
+
+__device__ __forceinline__ void wide_zero(WideAcc& w) {
+#pragma unroll
+    for (int i = 0; i < 17; i++) w.l[i] = 0;
+}
+
+// w += a * b   (integer product, 16 limbs): 64 IMAD.WIDE + 33 carry-chained adds
+__device__ __forceinline__ void wide_mac(WideAcc& w, const Fr& a, const Fr& b) { wide_mac_limbs(w.l, a.l, b.l); }
+
+// w += a * 2^256: after the final reduction this contributes exactly `a` (used for single-multiplicand products)
+__device__ __forceinline__ void wide_add_shifted(WideAcc& w, const Fr& a) {
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\t"
+        "addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.cc.u32 %4, %4, %13;\n\t"
+        "addc.cc.u32 %5, %5, %14;\n\t"
+        "addc.cc.u32 %6, %6, %15;\n\t"
+        "addc.cc.u32 %7, %7, %16;\n\t"
+        "addc.u32 %8, %8, 0;\n\t"
+        : "+r"(w.l[8]), "+r"(w.l[9]), "+r"(w.l[10]), "+r"(w.l[11]), "+r"(w.l[12]), "+r"(w.l[13]), "+r"(w.l[14]),
+          "+r"(w.l[15]), "+r"(w.l[16])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]));
+}
+
+__device__ __forceinline__ Fr R2() {  // R^2 mod p: mul(x, R2()) = x * R mod p for any x < 2^256
+    Fr r = {{0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u}};
+    return r;
+}
+
+// Montgomery-reduce a WideAcc (value V < 2^544) to the canonical field element V * R^-1 mod p.
+__device__ __forceinline__ Fr wide_reduce(const WideAcc& w) {
+    uint32_t ev[17], od[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) { ev[i] = w.l[i]; od[i] = 0; }
+    uint32_t c = redc_eo17(ev, od);
+    // quotient q = sum_{k=8..16} (ev[k] + od[k-1]) 2^(32(k-8)) + od[16] 2^288 + c  < 2^289: 10 limbs
+    uint32_t q[10];
+    asm("add.cc.u32 %0, %10, %19;\n\t"
+        "addc.cc.u32 %1, %11, %20;\n\t"
+        "addc.cc.u32 %2, %12, %21;\n\t"
+        "addc.cc.u32 %3, %13, %22;\n\t"
+        "addc.cc.u32 %4, %14, %23;\n\t"
+        "addc.cc.u32 %5, %15, %24;\n\t"
+        "addc.cc.u32 %6, %16, %25;\n\t"
+        "addc.cc.u32 %7, %17, %26;\n\t"
+        "addc.cc.u32 %8, %18, %27;\n\t"
+        "addc.u32 %9, %28, 0;\n\t"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9])
+        : "r"(ev[8]), "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]), "r"(ev[16]),
+          "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]), "r"(od[15]),
+          "r"(od[16]));
+    asm("add.cc.u32 %0, %0, %10;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.cc.u32 %7, %7, 0;\n\t"
+        "addc.cc.u32 %8, %8, 0;\n\t"
+        "addc.u32 %9, %9, 0;\n\t"
+        : "+r"(q[0]), "+r"(q[1]), "+r"(q[2]), "+r"(q[3]), "+r"(q[4]), "+r"(q[5]), "+r"(q[6]), "+r"(q[7]), "+r"(q[8]), "+r"(q[9])
+        : "r"(c));
+    // q = lo + hi * 2^256 with lo < 2^256 < 3p and hi < 2^64:  q mod p = (lo mod p) + hi*R mod p
+    Fr lo, hi = zero();
+#pragma unroll
+    for (int i = 0; i < 8; i++) lo.l[i] = q[i];
+    hi.l[0] = q[8];
+    hi.l[1] = q[9];
+    lo = reduce_once(reduce_once(lo));
+    return add(lo, mul(hi, R2()));
+}
+
 // Reference formulation in plain C (32-bit limbs, 64-bit accumulators); used by the micro-benchmark as a baseline.
 __device__ __forceinline__ Fr mul_c64(const Fr& a, const Fr& b) {
     const uint32_t P[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};

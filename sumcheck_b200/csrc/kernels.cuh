@@ -30,6 +30,7 @@ struct RoundParams {
     const uint8_t* prod_first;      // 1 where a CSR entry is the first use of its table (that use stores the fold)
     const uint32_t* coeffs;         // [n_products][8]
     uint32_t n_products;
+    uint32_t n_tables;
     uint32_t defer_coeff;           // single product: multiply the sums by coeffs[0] once at the end
     uint32_t t0;                    // first evaluation point of this launch
     uint32_t write_fold;            // store folded tables (only the t0 == 0 launch of a round does)
@@ -88,19 +89,30 @@ __device__ __forceinline__ Fr to_canonical(const Fr& a) {
 }
 
 template <int NPTS, bool FOLD>
-__global__ void __launch_bounds__(128) round_kernel(const RoundParams p) {
+__global__ void __launch_bounds__(128, 3) round_kernel(const RoundParams p) {
     __shared__ uint32_t s_red[32 * NPTS * 8];
     __shared__ bool s_last;
 
-    Fr acc[NPTS];
+    // Per-thread sums are kept UNREDUCED (fr::WideAcc): the last multiply of every product term is a plain 256x256-bit
+    // integer product added into 17 limbs; one Montgomery reduction per evaluation point per thread at the end.
+    fr::WideAcc accw[NPTS];
 #pragma unroll
-    for (int t = 0; t < NPTS; t++) acc[t] = fr::zero();
+    for (int t = 0; t < NPTS; t++) fr::wide_zero(accw[t]);
     Fr r;
 #pragma unroll
     for (int i = 0; i < 8; i++) r.l[i] = p.r[i];
 
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const uint32_t row_words = FOLD ? 32u : 16u;  // words of one table consumed per output pair
     for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < p.n_pairs; b += stride) {
+        // pull the rows of the NEXT grid-stride iteration into L2 now, so their HBM latency overlaps this iteration's
+        // ~10^4 cycles of arithmetic and the loads below mostly hit L2
+        if (b + stride < p.n_pairs) {
+            for (uint32_t j = 0; j < p.n_tables; j++) {
+                const uint32_t* nxt = p.tab_in[j] + (b + stride) * row_words;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+            }
+        }
         for (uint32_t k = 0; k < p.n_products; k++) {
             Fr prod[NPTS];
             const uint32_t j0 = p.prod_offsets[k], j1 = p.prod_offsets[k + 1];
@@ -128,15 +140,28 @@ __global__ void __launch_bounds__(128) round_kernel(const RoundParams p) {
                 Fr step = fr::sub(v1, v0);
                 Fr cur = v0;
                 for (uint32_t s = 0; s < p.t0; s++) cur = fr::add(cur, step);  // only for d+1 > MAX_NPTS
-                if (jj == j0) {
-                    if (!p.defer_coeff) {  // c_k * prod_j(...): scale the first multiplicand's line once
-                        Fr c = fr::load(p.coeffs + 8 * k);
-                        cur = fr::mul(cur, c);
-                        step = fr::mul(step, c);
+                const bool first = (jj == j0), last = (jj + 1 == j1);
+                if (first && !p.defer_coeff) {  // c_k * prod_j(...): scale the first multiplicand's line once
+                    Fr c = fr::load(p.coeffs + 8 * k);
+                    cur = fr::mul(cur, c);
+                    step = fr::mul(step, c);
+                }
+                if (first && last) {  // single multiplicand: contributes its value itself
+#pragma unroll
+                    for (int t = 0; t < NPTS; t++) {
+                        fr::wide_add_shifted(accw[t], cur);
+                        if (t + 1 < NPTS) cur = fr::add(cur, step);
                     }
+                } else if (first) {
 #pragma unroll
                     for (int t = 0; t < NPTS; t++) {
                         prod[t] = cur;
+                        if (t + 1 < NPTS) cur = fr::add(cur, step);
+                    }
+                } else if (last) {  // prover.rs:126-128 fused with the last multiply: products_sum[t] += product[t]*start
+#pragma unroll
+                    for (int t = 0; t < NPTS; t++) {
+                        fr::wide_mac(accw[t], prod[t], cur);
                         if (t + 1 < NPTS) cur = fr::add(cur, step);
                     }
                 } else {
@@ -147,10 +172,11 @@ __global__ void __launch_bounds__(128) round_kernel(const RoundParams p) {
                     }
                 }
             }
-#pragma unroll
-            for (int t = 0; t < NPTS; t++) acc[t] = fr::add(acc[t], prod[t]);  // prover.rs:126-128
         }
     }
+    Fr acc[NPTS];
+#pragma unroll
+    for (int t = 0; t < NPTS; t++) acc[t] = fr::wide_reduce(accw[t]);
 
     block_reduce<NPTS>(acc, s_red);
     if (threadIdx.x == 0) {

@@ -133,6 +133,7 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
     rp.prod_first = p->d_first;
     rp.coeffs = p->d_coeffs;
     rp.n_products = p->n_products;
+    rp.n_tables = p->T;
     rp.defer_coeff = (p->n_products == 1) ? 1u : 0u;
     rp.n_pairs = (unsigned long long)1 << (p->nv - i);
     if (fold) memcpy(rp.r, r, 32);
