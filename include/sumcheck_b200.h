@@ -112,6 +112,8 @@ size_t sc_serialize_proof(const uint64_t *evals, uint32_t nv, uint32_t d, uint8_
 /* Synthetic-input helper for benches and smoke runs (not part of the reference surface): fills `out` with n_elems
  * uniform Fr elements (Montgomery limbs) from a counter-based SplitMix64 stream — see sumcheck_b200/synth.py. */
 void sc_synth_table(uint64_t *out, uint64_t n_elems, uint64_t seed);
+/* elements [first_elem, first_elem + n_elems) of the same stream (a shard of a table) */
+void sc_synth_table_at(uint64_t *out, uint64_t first_elem, uint64_t n_elems, uint64_t seed);
 
 /* Per-round device timings of the last sc_ml_prove on this handle (ms, CUDA events on the launching stream):
  * copies min(nv, cap) values, returns nv. Kernel-only; excludes transcript/host time. */
@@ -142,6 +144,24 @@ int sc_gkr_start_phase2_sumcheck(sc_prover **out, uint32_t dim, const uint64_t *
 int sc_gkr_prove(sc_blake2b512_rng *rng, uint32_t dim, uint64_t nnz, const uint64_t *f1_idx, const uint64_t *f1_val,
                  const uint64_t *f2, const uint64_t *f3, const uint64_t *g, int device, uint64_t *phase1_out,
                  uint64_t *phase2_out, uint64_t *u_out, uint64_t *v_out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU).  The reference has no distributed path; this is the B200-native extension the
+ * north star asks for: every table is sharded by the HIGH log2(n_ranks) bits of the hypercube index, folds and sums
+ * stay local, and the only per-round exchange is the d+1 partial sums over NVLink.  All ranks call the same
+ * functions collectively and receive identical outputs. */
+#define SC_COMM_ID_BYTES 128
+typedef struct sc_comm sc_comm;
+/* Rank 0 creates an id and shares it with the other ranks through any channel the host application has. */
+int sc_comm_get_unique_id(uint8_t id_out[SC_COMM_ID_BYTES]);
+int sc_comm_create(sc_comm **out, const uint8_t id[SC_COMM_ID_BYTES], int rank, int n_ranks, int device);
+void sc_comm_destroy(sc_comm *c);
+/* prover_init over a sharded polynomial: `nv` is the GLOBAL number of variables; shard_tables[j] holds elements
+ * [rank*2^nv/n_ranks, (rank+1)*2^nv/n_ranks) of table j.  The handle then works with sc_prove_round / sc_ml_prove
+ * exactly like a single-GPU one (sc_prover_table returns this rank's shard while the rounds are still sharded). */
+int sc_prover_create_sharded(sc_prover **out, sc_comm *comm, uint32_t nv, uint32_t n_tables,
+                             const uint64_t *const *shard_tables, uint32_t n_products, const uint64_t *coeffs,
+                             const uint32_t *offsets, const uint32_t *indices);
 
 #ifdef __cplusplus
 }

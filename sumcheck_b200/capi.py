@@ -45,8 +45,14 @@ SIGNATURES = {
                                       U64P, U64P]),
     "sc_serialize_proof": (C.c_size_t, [U64P, C.c_uint32, C.c_uint32, U8P]),
     "sc_synth_table": (None, [U64P, C.c_uint64, C.c_uint64]),
+    "sc_synth_table_at": (None, [U64P, C.c_uint64, C.c_uint64, C.c_uint64]),
     "sc_prover_round_times_ms": (C.c_uint32, [C.c_void_p, F32P, C.c_uint32]),
     "sc_prover_launch_count": (C.c_uint64, [C.c_void_p]),
+    "sc_comm_get_unique_id": (C.c_int, [U8P]),
+    "sc_comm_create": (C.c_int, [C.POINTER(C.c_void_p), U8P, C.c_int, C.c_int, C.c_int]),
+    "sc_comm_destroy": (None, [C.c_void_p]),
+    "sc_prover_create_sharded": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p),
+                                           C.c_uint32, U64P, U32P, U32P]),
     "sc_gkr_initialize_phase_one": (C.c_int, [C.c_uint32, C.c_uint64, U64P, U64P, U64P, U64P, C.c_int, U64P, U64P, U64P, U64P]),
     "sc_gkr_initialize_phase_two": (C.c_int, [C.c_uint32, C.c_uint64, U64P, U64P, U64P, C.c_int, U64P]),
     "sc_gkr_start_phase1_sumcheck": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, U64P, U64P, C.c_int]),

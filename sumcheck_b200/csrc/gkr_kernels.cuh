@@ -127,6 +127,39 @@ __global__ void __launch_bounds__(128) to_canonical_kernel(const uint32_t* in, u
     }
 }
 
+// ---- multi-GPU helpers (capi_multi.inc)
+struct Fr8 {
+    uint32_t l[8];
+};
+// evals[t] = sum over ranks of gathered[g][t]  (+ canonical form for the transcript); npts <= 32
+__global__ void sum_partials_kernel(const uint32_t* gathered, uint32_t n_ranks, uint32_t npts, uint32_t* evals_out, uint32_t* canon_out) {
+    for (uint32_t t = threadIdx.x; t < npts; t += blockDim.x) {
+        Fr acc = fr::zero();
+        for (uint32_t g = 0; g < n_ranks; g++) acc = fr::add(acc, fr::load(gathered + ((size_t)g * npts + t) * 8));
+        fr::store(evals_out + (size_t)t * 8, acc);
+        Fr one_int = fr::zero();
+        one_int.l[0] = 1;
+        fr::store(canon_out + (size_t)t * 8, fr::mul(acc, one_int));
+    }
+}
+// out[j] = tab[j][0] + r * (tab[j][1] - tab[j][0])  for the T two-entry tables of a shard
+__global__ void fold_final_kernel(const uint32_t* const* tabs, uint32_t T, Fr8 r8, uint32_t* out) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= T) return;
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = r8.l[i];
+    Fr a = fr::load(tabs[j]), b = fr::load(tabs[j] + 8);
+    fr::store(out + (size_t)j * 8, fr::add(a, fr::mul(r, fr::sub(b, a))));
+}
+// gathered[g][j] -> tables[j][g]
+__global__ void transpose_gather_kernel(const uint32_t* gathered, uint32_t n_ranks, uint32_t T, uint32_t* tables) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ranks * T) return;
+    uint32_t g = i / T, j = i % T;
+    fr::store(tables + ((size_t)j * n_ranks + g) * 8, fr::load(gathered + (size_t)i * 8));
+}
+
 // ---- merged sparse output for the stand-alone initialize_phase_one API: after sorting (key, position) by key,
 // flag segment heads, and let one thread per head sum its segment.
 __global__ void __launch_bounds__(128) seg_heads_kernel(const unsigned long long* keys, unsigned long long n, uint32_t* head) {

@@ -88,6 +88,16 @@ struct sc_prover {
     std::vector<float> round_ms;
     bool timing = false;
     uint64_t launches = 0;
+    // where the d+1 results of the last round live on the device (local buffers, the summed copies, or the sub-prover's)
+    uint32_t *out_evals = nullptr, *out_canon = nullptr;
+    // ---- multi-GPU (capi_multi.inc): nv is GLOBAL, nv_local = nv - log2(ranks) is what this rank's shard spans
+    uint32_t nv_local = 0;
+    struct sc_comm* comm = nullptr;
+    sc_prover* sub = nullptr;  // replicated prover for the last log2(ranks) rounds
+    uint32_t *d_gather = nullptr, *d_evals_g = nullptr, *d_canon_g = nullptr, *d_fold = nullptr, *d_gather_tabs = nullptr,
+             *d_sub_tabs = nullptr;
+    std::vector<uint64_t> h_coeffs;
+    std::vector<uint32_t> h_offsets, h_indices;
 };
 
 namespace {
@@ -135,7 +145,7 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
     rp.n_products = p->n_products;
     rp.n_tables = p->T;
     rp.defer_coeff = (p->n_products == 1) ? 1u : 0u;
-    rp.n_pairs = (unsigned long long)1 << (p->nv - i);
+    rp.n_pairs = (unsigned long long)1 << (p->nv_local - i);
     if (fold) memcpy(rp.r, r, 32);
     rp.partials = p->d_partials;
     rp.counter = p->d_counter;
@@ -190,7 +200,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     rc = ensure_device(device);
     if (rc) return rc;
     sc_prover* p = new sc_prover();
-    p->device = device; p->nv = nv; p->T = T; p->n_products = n_products; p->d = d; p->N = (uint64_t)1 << nv;
+    p->device = device; p->nv = nv; p->nv_local = nv; p->T = T; p->n_products = n_products; p->d = d; p->N = (uint64_t)1 << nv;
     auto bail = [&](int code) { sc_prover_destroy(p); return code; };
 #define TRY_P(expr)                                                                                        \
     do {                                                                                                   \
@@ -258,6 +268,8 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     return SC_OK;
 }
 
+int sharded_round(sc_prover* p, const uint64_t* r);  // capi_multi.inc
+
 // prove_round state machine (prover.rs:78-98) + device round + D2H of the d+1 results into the pinned buffers.
 int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
     if (r_or_null) {
@@ -271,12 +283,19 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
     CUDA_TRY(cudaSetDevice(p->device));
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1)], p->stream));
     // prover.rs:85-86: r = randomness[round-1] — the challenge just pushed
-    int rc = run_round_device(p, r_or_null);
+    int rc;
+    if (p->comm) {
+        rc = sharded_round(p, r_or_null);
+    } else {
+        rc = run_round_device(p, r_or_null);
+        p->out_evals = p->d_evals;
+        p->out_canon = p->d_canon;
+    }
     if (rc) return rc;
     if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));
     const size_t bytes = (size_t)(p->d + 1) * 32;
-    CUDA_TRY(cudaMemcpyAsync(p->h_evals, p->d_evals, bytes, cudaMemcpyDeviceToHost, p->stream));
-    CUDA_TRY(cudaMemcpyAsync(p->h_canon, p->d_canon, bytes, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->h_evals, p->out_evals, bytes, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->h_canon, p->out_canon, bytes, cudaMemcpyDeviceToHost, p->stream));
     if (sync_out) CUDA_TRY(cudaStreamSynchronize(p->stream));
     return SC_OK;
 }
@@ -339,6 +358,9 @@ void sc_prover_destroy(sc_prover* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->sub) { p->sub->stream = p->sub->own_stream; sc_prover_destroy(p->sub); cudaSetDevice(p->device); }
+    cudaFree(p->d_gather); cudaFree(p->d_evals_g); cudaFree(p->d_canon_g); cudaFree(p->d_fold); cudaFree(p->d_gather_tabs);
+    cudaFree(p->d_sub_tabs);
     if (p->owns_tab0) cudaFree(p->slab0);
     cudaFree(p->slabA); cudaFree(p->slabB);
     cudaFree(p->d_ptr0); cudaFree(p->d_ptrA); cudaFree(p->d_ptrB);
@@ -400,7 +422,9 @@ int sc_prover_push_randomness(sc_prover* p, const uint64_t r[4]) {
 int sc_prover_table(const sc_prover* p, uint32_t j, uint64_t* out, uint64_t cap_elems, uint64_t* len_out) {
     if (j >= p->T) return fail(SC_ERR_BAD_INPUT, "table %u out of range", j);
     // after round i >= 2 the tables have been folded i-1 times
-    uint64_t len = p->round <= 1 ? p->N : (p->N >> (p->round - 1));
+    if (p->comm && p->round > p->nv_local)
+        return fail(SC_ERR_BAD_INPUT, "sharded prover: tables are replicated on the sub-prover after round %u", p->nv_local);
+    uint64_t len = p->round <= 1 ? p->N : (p->N >> (p->round - 1));  // sharded: this rank's shard
     if (len_out) *len_out = len;
     if (!out) return SC_OK;
     if (cap_elems < len) return fail(SC_ERR_BAD_INPUT, "buffer too small: %llu < %llu", (unsigned long long)cap_elems, (unsigned long long)len);
@@ -441,7 +465,9 @@ int sc_ml_prove_oneshot(uint32_t nv, uint32_t n_tables, const uint64_t* const* t
 
 size_t sc_serialize_proof(const uint64_t* evals, uint32_t nv, uint32_t d, uint8_t* out);  // defined in gkr/serialize section
 
-void sc_synth_table(uint64_t* out, uint64_t n_elems, uint64_t seed) {
+void sc_synth_table(uint64_t* out, uint64_t n_elems, uint64_t seed) { sc_synth_table_at(out, 0, n_elems, seed); }
+
+void sc_synth_table_at(uint64_t* out, uint64_t first_elem, uint64_t n_elems, uint64_t seed) {
     const uint64_t GAMMA = 0x9e3779b97f4a7c15ULL;
     const uint64_t P[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
     auto mix = [](uint64_t z) {
@@ -449,7 +475,8 @@ void sc_synth_table(uint64_t* out, uint64_t n_elems, uint64_t seed) {
         z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
         return z ^ (z >> 31);
     };
-    for (uint64_t e = 0; e < n_elems; e++) {
+    for (uint64_t e0 = 0; e0 < n_elems; e0++) {
+        const uint64_t e = first_elem + e0;
         uint64_t t[4];
         for (uint64_t k = 0; k < 8; k++) {
             for (uint64_t i = 0; i < 4; i++) t[i] = mix(seed + GAMMA * (((e * 8 + k) * 4) + i + 1));
@@ -462,7 +489,7 @@ void sc_synth_table(uint64_t* out, uint64_t n_elems, uint64_t seed) {
             if (lt) break;
             if (k == 7) t[3] &= 0x3fffffffffffffffULL;
         }
-        memcpy(out + 4 * e, t, 32);
+        memcpy(out + 4 * e0, t, 32);
     }
 }
 
@@ -476,3 +503,4 @@ uint64_t sc_prover_launch_count(const sc_prover* p) { return p->launches; }
 }  // extern "C"
 
 #include "capi_gkr.inc"
+#include "capi_multi.inc"

@@ -53,13 +53,14 @@ def synth_table(n_elems, seed, out=None, chunk=1 << 20):
     return out
 
 
-def synth_table_fast(n_elems, seed, out=None):
-    """Same stream through the C helper sc_synth_table (scalar C, ~10x faster than the numpy twin)."""
+def synth_table_fast(n_elems, seed, out=None, first=0):
+    """Same stream through the C helper sc_synth_table_at (scalar C, ~10x faster than the numpy twin); `first` selects
+    the slice [first, first + n_elems) of the table, e.g. one rank's shard."""
     import ctypes as C
 
     from . import capi
     if out is None:
         out = np.empty((n_elems, 4), dtype=np.uint64)
     assert out.dtype == np.uint64 and out.flags["C_CONTIGUOUS"] and out.shape == (n_elems, 4)
-    capi.lib().sc_synth_table(out.ctypes.data_as(capi.U64P), C.c_uint64(n_elems), C.c_uint64(seed))
+    capi.lib().sc_synth_table_at(out.ctypes.data_as(capi.U64P), C.c_uint64(first), C.c_uint64(n_elems), C.c_uint64(seed))
     return out
