@@ -138,8 +138,11 @@ __device__ __forceinline__ Fr sub(const Fr& a, const Fr& b) {
     return t;
 }
 
-// Montgomery product a*b*2^-256 mod p: 64 IMAD.WIDE for the product + 56 for the reduction.
-__device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) {
+#ifndef FR_MUL_INLINE
+#define FR_MUL_INLINE __forceinline__
+#endif
+// Montgomery product a*b*2^-256 mod p: 63 IMAD.WIDE for the product + 48 for the reduction.
+__device__ FR_MUL_INLINE Fr mul(const Fr& a, const Fr& b) {
     uint32_t ev[16], od[16];
     mul_wide_eo(ev, od, a.l, b.l);
     uint32_t c = redc_eo(ev, od);
@@ -185,7 +188,7 @@ __device__ __forceinline__ void wide_zero(WideAcc& w) {
 }
 
 // w += a * b   (integer product, 16 limbs): 64 IMAD.WIDE + 33 carry-chained adds
-__device__ __forceinline__ void wide_mac(WideAcc& w, const Fr& a, const Fr& b) { wide_mac_limbs(w.l, a.l, b.l); }
+__device__ FR_MUL_INLINE void wide_mac(WideAcc& w, const Fr& a, const Fr& b) { wide_mac_limbs(w.l, a.l, b.l); }
 
 // w += a * 2^256: after the final reduction this contributes exactly `a` (used for single-multiplicand products)
 __device__ __forceinline__ void wide_add_shifted(WideAcc& w, const Fr& a) {

@@ -16,7 +16,7 @@ out = []
 emit = out.append
 
 
-def asm_block(lines, outs, ins, indent="    "):
+def asm_block(lines, outs, ins, indent="    ", fresh=()):
     """outs: list of C lvalues used as "+r"; ins: list of C rvalues used as "r". `lines` use {o0}.. / {i0}.. names."""
     names = {}
     for k, _ in enumerate(outs):
@@ -25,16 +25,24 @@ def asm_block(lines, outs, ins, indent="    "):
         names[f"i{k}"] = f"%{len(outs) + k}"
     assert len(outs) + len(ins) <= 30, "asm operand limit"
     body = "\n".join(f'{indent}    "{ln.format(**names)};\\n\\t"' for ln in lines)
-    o = ", ".join(f'"+r"({x})' for x in outs)
+    o = ", ".join((f'"=r"({x})' if x in fresh else f'"+r"({x})') for x in outs)
     i = ", ".join(f'"r"({x})' for x in ins)
     emit(f"{indent}asm(\n{body}\n{indent}    : {o}\n{indent}    : {i});")
 
 
-def chain(acc, base, n_prod, a_ops, b_op, prop_to, first_is_mul=False, first_pair=None):
+WRITTEN = None  # when a dict {"ev": set, "od": set}: track first touches so fresh limbs are produced, not accumulated
+
+
+def chain(acc, base, n_prod, a_ops, b_op, prop_to, first_is_mul=False, first_pair=None, fresh=()):
     """acc[base .. base+2*n_prod) += a_ops[k] * b_op (k-th product on limbs base+2k, base+2k+1), carry chained, then
     carry propagated through acc[base+2*n_prod .. prop_to] (inclusive)."""
     outs = [f"{acc}[{base + k}]" for k in range(2 * n_prod)]
     tail = [f"{acc}[{k}]" for k in range(base + 2 * n_prod, prop_to + 1)]
+    if WRITTEN is not None:
+        touched = list(range(base, base + 2 * n_prod)) + list(range(base + 2 * n_prod, prop_to + 1))
+        fresh = tuple(k for k in touched if k not in WRITTEN[acc])
+        WRITTEN[acc].update(touched)
+    fresh_names = {f"{acc}[{k}]" for k in fresh}
     ins = list(a_ops) + [b_op]
     nb = len(a_ops)
     if first_pair:
@@ -44,6 +52,8 @@ def chain(acc, base, n_prod, a_ops, b_op, prop_to, first_is_mul=False, first_pai
         lo, hi = f"{{o{2 * k}}}", f"{{o{2 * k + 1}}}"
         a, b = f"{{i{k}}}", f"{{i{nb}}}"
         last = (k == n_prod - 1) and not tail
+        if first_is_mul:
+            fresh_names.update(outs)
         if k == 0 and first_pair:
             # the product a_ops[0]*b_op is supplied as a ready (lo, hi) pair: two carry-chained adds, no multiply
             lines.append(f"add.cc.u32 {lo}, {lo}, {{i{nb + 1}}}")
@@ -52,12 +62,15 @@ def chain(acc, base, n_prod, a_ops, b_op, prop_to, first_is_mul=False, first_pai
             lines.append(f"mul.lo.u32 {lo}, {a}, {b}")
             lines.append(f"mul.hi.u32 {hi}, {a}, {b}")
         else:
-            lines.append(("mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32") + f" {lo}, {a}, {b}, {lo}")
-            lines.append(("madc.hi.u32" if last else "madc.hi.cc.u32") + f" {hi}, {a}, {b}, {hi}")
-    for k, _ in enumerate(tail):
+            lo_add = "0" if outs[2 * k] in fresh_names else lo
+            hi_add = "0" if outs[2 * k + 1] in fresh_names else hi
+            lines.append(("mad.lo.cc.u32" if k == 0 else "madc.lo.cc.u32") + f" {lo}, {a}, {b}, {lo_add}")
+            lines.append(("madc.hi.u32" if last else "madc.hi.cc.u32") + f" {hi}, {a}, {b}, {hi_add}")
+    for k, t in enumerate(tail):
         o = f"{{o{2 * n_prod + k}}}"
-        lines.append(("addc.u32" if k == len(tail) - 1 else "addc.cc.u32") + f" {o}, {o}, 0")
-    asm_block(lines, outs + tail, ins)
+        src = "0" if t in fresh_names else o
+        lines.append(("addc.u32" if k == len(tail) - 1 else "addc.cc.u32") + f" {o}, {src}, 0")
+    asm_block(lines, outs + tail, ins, fresh=fresh_names)
 
 
 def add_chain(dst, src, cin=None, cout=None, indent="    "):
@@ -106,8 +119,8 @@ emit("")
 emit("// ev[k] = limb k of the EVEN accumulator, od[k] = limb k+1 of the ODD accumulator; a*b = EV + OD*2^32.")
 emit("// Every chain's (lo,hi) destination pair starts on an even index, so ptxas emits IMAD.WIDE.U32(.X).")
 emit("__device__ __forceinline__ void mul_wide_eo(uint32_t (&ev)[16], uint32_t (&od)[16], const uint32_t (&a)[8], const uint32_t (&b)[8]) {")
-emit("#pragma unroll")
-emit("    for (int k = 8; k < 16; k++) { ev[k] = 0; od[k] = 0; }")
+emit("    od[15] = 0;  // every other limb is produced (not accumulated) on first touch")
+WRITTEN = {"ev": set(), "od": set()}
 A_EVEN = ["a[0]", "a[2]", "a[4]", "a[6]"]
 A_ODD = ["a[1]", "a[3]", "a[5]", "a[7]"]
 # row 0: plain products
@@ -122,6 +135,8 @@ for i in range(1, 8):
     else:
         chain("ev", i, 4, A_EVEN, f"b[{i}]", i + 8)
         chain("od", i, 4, A_ODD, f"b[{i}]", -1)
+assert WRITTEN["ev"] == set(range(16)) and WRITTEN["od"] == set(range(15)), WRITTEN
+WRITTEN = None
 emit("}")
 emit("")
 

@@ -14,6 +14,10 @@ namespace sck {
 
 using fr::Fr;
 
+struct Fr8 {  // a field element passed by value as a kernel argument
+    uint32_t l[8];
+};
+
 __device__ __forceinline__ Fr fr_R2() {  // R^2 mod p: mul(x, R2) = x*R mod p
     Fr r = {{0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u}};
     return r;
@@ -128,14 +132,26 @@ __global__ void __launch_bounds__(128) to_canonical_kernel(const uint32_t* in, u
 }
 
 // ---- multi-GPU helpers (capi_multi.inc)
-struct Fr8 {
-    uint32_t l[8];
-};
-// evals[t] = sum over ranks of gathered[g][t]  (+ canonical form for the transcript); npts <= 32
-__global__ void sum_partials_kernel(const uint32_t* gathered, uint32_t n_ranks, uint32_t npts, uint32_t* evals_out, uint32_t* canon_out) {
-    for (uint32_t t = threadIdx.x; t < npts; t += blockDim.x) {
-        Fr acc = fr::zero();
+// evals[t] = sum over ranks of gathered[g][t]  (+ canonical form for the transcript); npts <= 32, one warp.
+// fix1: the ranks summed only t = 0, 2, .., d (slot 1 is zero); P(1) = P_prev(r) - P(0) with P_prev = evals_out's old content.
+__global__ void sum_partials_kernel(const uint32_t* gathered, uint32_t n_ranks, uint32_t npts, uint32_t* evals_out, uint32_t* canon_out,
+                                    uint32_t fix1, Fr8 r8, const uint32_t* lagrange) {
+    __shared__ uint32_t scratch[32 * 8];
+    const uint32_t t = threadIdx.x;
+    Fr r, claim = fr::zero();
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = r8.l[i];
+    if (fix1) claim = claim_from_prev(evals_out, lagrange, r, npts - 1, scratch);
+    Fr acc = fr::zero();
+    if (t < npts)
         for (uint32_t g = 0; g < n_ranks; g++) acc = fr::add(acc, fr::load(gathered + ((size_t)g * npts + t) * 8));
+    if (fix1) {  // lane 1 needs lane 0's P(0) and claim
+        Fr p0, cl;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { p0.l[i] = __shfl_sync(0xffffffffu, acc.l[i], 0); cl.l[i] = __shfl_sync(0xffffffffu, claim.l[i], 0); }
+        if (t == 1) acc = fr::sub(cl, p0);
+    }
+    if (t < npts) {
         fr::store(evals_out + (size_t)t * 8, acc);
         Fr one_int = fr::zero();
         one_int.l[0] = 1;

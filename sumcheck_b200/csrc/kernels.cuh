@@ -40,7 +40,40 @@ struct RoundParams {
     unsigned int* counter;          // last-block election
     uint32_t* evals_out;            // [(d+1)][8] Montgomery — ProverMsg.evaluations
     uint32_t* canon_out;            // [(d+1)][8] canonical integers (what ark-serialize writes to the transcript)
+    // P(1) from the previous round's claim (rounds >= 2, single launch per round): the launch sums the points
+    // t = 0, 2, 3, .., d only (skip1) and, when fix1 is set, the last block fills P(1) = P_prev(r) - P(0).
+    uint32_t skip1, fix1, degree;
+    const uint32_t* prev_evals;     // [(d+1)][8] previous round's ProverMsg (may alias evals_out: read first)
+    const uint32_t* lagrange;       // [2][(d+1)][8]: w_j = 1/prod_{k!=j}(j-k), then the field elements 0..d
 };
+
+// P_prev(r) by Lagrange interpolation through (j, prev[j]), j = 0..d — what the verifier computes at
+// verifier.rs:114 (interpolate_uni_poly); exact field arithmetic, so any evaluation order gives the same element.
+// Called by one whole warp; lanes j <= d each build one term; result valid in lane 0.  scratch: >= (d+1)*8 words.
+__device__ __forceinline__ Fr claim_from_prev(const uint32_t* prev, const uint32_t* lagr, const Fr& r, uint32_t d, uint32_t* scratch) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (lane <= d) {
+        Fr term = fr::mul(fr::load(prev + lane * 8), fr::load(lagr + lane * 8));
+        for (uint32_t k = 0; k <= d; k++) {
+            if (k == lane) continue;
+            term = fr::mul(term, fr::sub(r, fr::load(lagr + (size_t)(d + 1 + k) * 8)));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) scratch[lane * 8 + i] = term.l[i];
+    }
+    __syncwarp();
+    Fr acc = fr::zero();
+    if (lane == 0) {
+        for (uint32_t j = 0; j <= d; j++) {
+            Fr t;
+#pragma unroll
+            for (int i = 0; i < 8; i++) t.l[i] = scratch[j * 8 + i];
+            acc = fr::add(acc, t);
+        }
+    }
+    __syncwarp();
+    return acc;
+}
 
 // ---- block-wide sum of NPTS field elements per thread; result valid in thread 0 ------------------------------
 __device__ __forceinline__ Fr shfl_down(const Fr& v, int delta) {
@@ -146,31 +179,38 @@ __global__ void __launch_bounds__(128, 3) round_kernel(const RoundParams p) {
                     cur = fr::mul(cur, c);
                     step = fr::mul(step, c);
                 }
+                // slot s holds evaluation point t0+s, or with skip1 the points 0, 2, 3, ..: one extra step after slot 0
+#define SC_NEXT_POINT(t)                                        \
+    if ((t) + 1 < NPTS) {                                       \
+        cur = fr::add(cur, step);                               \
+        if ((t) == 0 && p.skip1) cur = fr::add(cur, step);      \
+    }
                 if (first && last) {  // single multiplicand: contributes its value itself
 #pragma unroll
                     for (int t = 0; t < NPTS; t++) {
                         fr::wide_add_shifted(accw[t], cur);
-                        if (t + 1 < NPTS) cur = fr::add(cur, step);
+                        SC_NEXT_POINT(t)
                     }
                 } else if (first) {
 #pragma unroll
                     for (int t = 0; t < NPTS; t++) {
                         prod[t] = cur;
-                        if (t + 1 < NPTS) cur = fr::add(cur, step);
+                        SC_NEXT_POINT(t)
                     }
                 } else if (last) {  // prover.rs:126-128 fused with the last multiply: products_sum[t] += product[t]*start
 #pragma unroll
                     for (int t = 0; t < NPTS; t++) {
                         fr::wide_mac(accw[t], prod[t], cur);
-                        if (t + 1 < NPTS) cur = fr::add(cur, step);
+                        SC_NEXT_POINT(t)
                     }
                 } else {
 #pragma unroll
                     for (int t = 0; t < NPTS; t++) {
                         prod[t] = fr::mul(prod[t], cur);
-                        if (t + 1 < NPTS) cur = fr::add(cur, step);
+                        SC_NEXT_POINT(t)
                     }
                 }
+#undef SC_NEXT_POINT
             }
         }
     }
@@ -199,16 +239,50 @@ __global__ void __launch_bounds__(128, 3) round_kernel(const RoundParams p) {
         for (int t = 0; t < NPTS; t++) acc[t] = fr::add(acc[t], fr::load(p.partials + ((size_t)g * NPTS + t) * 8));
     }
     block_reduce<NPTS>(acc, s_red);
+    if (threadIdx.x >= 32) return;
+    Fr claim = fr::zero();
+    if (p.fix1) claim = claim_from_prev(p.prev_evals, p.lagrange, r, p.degree, s_red);  // reads prev before it is overwritten
     if (threadIdx.x == 0) {
         Fr c = fr::load(p.coeffs);
 #pragma unroll
         for (int t = 0; t < NPTS; t++) {
             Fr v = p.defer_coeff ? fr::mul(acc[t], c) : acc[t];
-            fr::store(p.evals_out + (size_t)(p.t0 + t) * 8, v);
-            fr::store(p.canon_out + (size_t)(p.t0 + t) * 8, to_canonical(v));
+            const uint32_t slot = p.skip1 ? (t == 0 ? 0u : (uint32_t)t + 1u) : p.t0 + (uint32_t)t;
+            fr::store(p.evals_out + (size_t)slot * 8, v);
+            fr::store(p.canon_out + (size_t)slot * 8, to_canonical(v));
+            if (t == 0 && p.skip1) {  // P(1) = claim - P(0); without fix1 (sharded) slot 1 stays zero for the all-gather
+                Fr p1 = p.fix1 ? fr::sub(claim, v) : fr::zero();
+                fr::store(p.evals_out + 8, p1);
+                fr::store(p.canon_out + 8, to_canonical(p1));
+            }
         }
         *p.counter = 0;
     }
+}
+
+// Lagrange data for claim_from_prev: w_j = 1 / prod_{k != j} (j - k) and the field elements 0..d (one thread per j).
+__global__ void lagrange_setup_kernel(uint32_t d, uint32_t* out) {
+    const uint32_t j = threadIdx.x;
+    if (j > d) return;
+    Fr r2 = {{0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u}};
+    Fr raw = fr::zero();
+    raw.l[0] = j;
+    const Fr fj = fr::mul(raw, r2);  // j in Montgomery form
+    fr::store(out + (size_t)(d + 1 + j) * 8, fj);
+    Fr den = fr::one();
+    for (uint32_t k = 0; k <= d; k++) {
+        if (k == j) continue;
+        raw.l[0] = k;
+        den = fr::mul(den, fr::sub(fj, fr::mul(raw, r2)));
+    }
+    // den^(p-2) by square-and-multiply, p - 2 = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfefffffffeffffffff
+    const uint32_t e[8] = {0xffffffffu, 0xfffffffeu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+    Fr acc = fr::one();
+    for (int i = 255; i >= 0; i--) {
+        acc = fr::mul(acc, acc);
+        if ((e[i >> 5] >> (i & 31)) & 1) acc = fr::mul(acc, den);
+    }
+    fr::store(out + (size_t)j * 8, acc);
 }
 
 }  // namespace sck

@@ -77,7 +77,7 @@ struct sc_prover {
     uint32_t** d_ptrB = nullptr;
     uint32_t *d_offsets = nullptr, *d_indices = nullptr, *d_coeffs = nullptr;
     uint8_t* d_first = nullptr;
-    uint32_t *d_partials = nullptr, *d_evals = nullptr, *d_canon = nullptr;
+    uint32_t *d_partials = nullptr, *d_evals = nullptr, *d_canon = nullptr, *d_lagrange = nullptr;
     unsigned int* d_counter = nullptr;
     uint32_t *h_evals = nullptr, *h_canon = nullptr;  // pinned
     int max_grid = 0;
@@ -87,6 +87,7 @@ struct sc_prover {
     std::vector<cudaEvent_t> ev;  // 2 per round
     std::vector<float> round_ms;
     bool timing = false;
+    bool used_skip1 = false;  // last device round summed t = 0, 2, .., d only
     uint64_t launches = 0;
     // where the d+1 results of the last round live on the device (local buffers, the summed copies, or the sub-prover's)
     uint32_t *out_evals = nullptr, *out_canon = nullptr;
@@ -151,6 +152,29 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
     rp.counter = p->d_counter;
     rp.evals_out = p->d_evals;
     rp.canon_out = p->d_canon;
+    rp.degree = p->d;
+    rp.prev_evals = p->d_evals;
+    rp.lagrange = p->d_lagrange;
+    if (fold && p->d <= (uint32_t)sck::MAX_NPTS && p->d_lagrange) {
+        // rounds >= 2: P(0) + P(1) = P_prev(r) (the verifier's check, verifier.rs:109), so only t = 0, 2, .., d are summed
+        rp.skip1 = 1;
+        rp.fix1 = p->comm ? 0u : 1u;  // sharded: the fix needs the GLOBAL P(0) -> done after the all-gather
+        rp.t0 = 0;
+        rp.write_fold = 1;
+        cudaError_t e;
+        switch (p->d) {
+            case 1: e = launch_round<1>(p, true, rp); break;
+            case 2: e = launch_round<2>(p, true, rp); break;
+            case 3: e = launch_round<3>(p, true, rp); break;
+            case 4: e = launch_round<4>(p, true, rp); break;
+            default: e = launch_round<5>(p, true, rp); break;
+        }
+        if (e != cudaSuccess) return fail(SC_ERR_CUDA, "round kernel launch: %s", cudaGetErrorString(e));
+        p->cur = next;
+        p->used_skip1 = true;
+        return SC_OK;
+    }
+    p->used_skip1 = false;
     uint32_t remaining = p->d + 1, t0 = 0;
     while (remaining > 0) {
         uint32_t take;
@@ -256,6 +280,11 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     TRY_P(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned int), p->stream));
     TRY_P(cudaMalloc(&p->d_evals, (size_t)(d + 1) * 32));
     TRY_P(cudaMalloc(&p->d_canon, (size_t)(d + 1) * 32));
+    if (d + 1 <= 32) {  // Lagrange weights for the P(1)-from-claim shortcut
+        TRY_P(cudaMalloc(&p->d_lagrange, (size_t)2 * (d + 1) * 32));
+        sck::lagrange_setup_kernel<<<1, 32, 0, p->stream>>>(d, p->d_lagrange);
+        TRY_P(cudaGetLastError());
+    }
     TRY_P(cudaMallocHost(&p->h_evals, (size_t)(d + 1) * 32));
     TRY_P(cudaMallocHost(&p->h_canon, (size_t)(d + 1) * 32));
     p->ev.resize(2 * (size_t)nv);
@@ -365,7 +394,7 @@ void sc_prover_destroy(sc_prover* p) {
     cudaFree(p->slabA); cudaFree(p->slabB);
     cudaFree(p->d_ptr0); cudaFree(p->d_ptrA); cudaFree(p->d_ptrB);
     cudaFree(p->d_offsets); cudaFree(p->d_indices); cudaFree(p->d_first); cudaFree(p->d_coeffs);
-    cudaFree(p->d_partials); cudaFree(p->d_counter); cudaFree(p->d_evals); cudaFree(p->d_canon);
+    cudaFree(p->d_partials); cudaFree(p->d_counter); cudaFree(p->d_evals); cudaFree(p->d_canon); cudaFree(p->d_lagrange);
     if (p->h_evals) cudaFreeHost(p->h_evals);
     if (p->h_canon) cudaFreeHost(p->h_canon);
     for (auto e : p->ev) if (e) cudaEventDestroy(e);
