@@ -160,11 +160,16 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         prove_resident()
-        round_ms += st.round_times_ms()
     e1.record(stream)
     torch.cuda.synchronize()
     ms_step = e0.elapsed_time(e1) / args.steps
     launches = st.launch_count()
+    # per-round kernel times (CUDA events on the launching stream) from extra, separately instrumented steps
+    st.set_timing(True)
+    for _ in range(args.steps):
+        prove_resident()
+        round_ms += st.round_times_ms()
+    st.set_timing(False)
     round_ms /= args.steps
     first = evals.copy()
 

@@ -115,6 +115,8 @@ void sc_synth_table(uint64_t *out, uint64_t n_elems, uint64_t seed);
 /* elements [first_elem, first_elem + n_elems) of the same stream (a shard of a table) */
 void sc_synth_table_at(uint64_t *out, uint64_t first_elem, uint64_t n_elems, uint64_t seed);
 
+/* Enable (1) / disable (0, default) per-round CUDA-event timing of sc_ml_prove / sc_gkr phases on this handle. */
+int sc_prover_set_timing(sc_prover *p, int enabled);
 /* Per-round device timings of the last sc_ml_prove on this handle (ms, CUDA events on the launching stream):
  * copies min(nv, cap) values, returns nv. Kernel-only; excludes transcript/host time. */
 uint32_t sc_prover_round_times_ms(const sc_prover *p, float *out, uint32_t cap);

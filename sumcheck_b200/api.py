@@ -243,6 +243,9 @@ class ProverState:
         """sc_ml_prove on this (round-0) handle into a preallocated [nv, d+1, 4] array."""
         _check(capi.lib().sc_ml_prove(self._h, C.byref(rng.state), _p64(evals), None))
 
+    def set_timing(self, enabled):
+        _check(capi.lib().sc_prover_set_timing(self._h, 1 if enabled else 0))
+
     def round_times_ms(self):
         nv = self.num_vars
         out = np.zeros(nv, dtype=np.float32)

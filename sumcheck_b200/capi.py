@@ -46,6 +46,7 @@ SIGNATURES = {
     "sc_serialize_proof": (C.c_size_t, [U64P, C.c_uint32, C.c_uint32, U8P]),
     "sc_synth_table": (None, [U64P, C.c_uint64, C.c_uint64]),
     "sc_synth_table_at": (None, [U64P, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "sc_prover_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "sc_prover_round_times_ms": (C.c_uint32, [C.c_void_p, F32P, C.c_uint32]),
     "sc_prover_launch_count": (C.c_uint64, [C.c_void_p]),
     "sc_comm_get_unique_id": (C.c_int, [U8P]),

@@ -164,3 +164,108 @@ SC_HD inline void put_u64(uint8_t* o, uint64_t v) {
 }
 
 }  // namespace b2
+
+// ---------------------------------------------------------------------------------------------------------------
+// Word-oriented device transcript for the fused tail kernel (kernels.cuh, tail_kernel): every message of
+// MLSumcheck::prove is a whole number of 64-bit words (PolynomialInfo 16 B, ProverMsg 8+32(d+1) B, digests 64 B), so the
+// 128-byte block buffer is kept as 16 u64 words in shared memory and one thread drives it.  Only usable when the
+// state handed over by the host has buflen % 8 == 0 (otherwise the host keeps the transcript).
+#ifdef __CUDACC__
+namespace b2w {
+
+struct WState {       // lives in shared memory
+    uint64_t h[8];
+    uint64_t t0;      // bytes compressed so far (low word; a sumcheck transcript never reaches 2^64 bytes)
+    uint64_t buf[16];
+    uint32_t nwords;  // words currently in buf (0..16)
+    uint64_t fh[8];   // scratch for finalisation: chaining value copy
+    uint64_t fblk[16];  //                         zero-padded last block
+};
+
+__constant__ uint8_t SIGMA[12][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0},
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3}};
+
+// One compression, ROLLED over the 12 rounds and never inlined: the tail kernel calls it ~7 times per protocol round
+// from a single thread, so what matters is that its ~300 instructions stay hot in the instruction cache (the fully
+// unrolled form is ~40 KB of straight-line code and ran 10x slower because every fetch missed).
+// m: the 16 message words (shared memory; indexed through SIGMA).
+static __device__ __noinline__ void compress_words(uint64_t* h, const uint64_t* m, uint64_t t0, bool last) {
+    using b2::rotr64;
+    uint64_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
+    uint64_t v8 = b2::iv(0), v9 = b2::iv(1), v10 = b2::iv(2), v11 = b2::iv(3), v12 = b2::iv(4) ^ t0, v13 = b2::iv(5),
+             v14 = last ? ~b2::iv(6) : b2::iv(6), v15 = b2::iv(7);
+#pragma unroll 1
+    for (int r = 0; r < 12; r++) {
+        const uint8_t* s = SIGMA[r];
+        B2_G(v0, v4, v8, v12, m[s[0]], m[s[1]]);
+        B2_G(v1, v5, v9, v13, m[s[2]], m[s[3]]);
+        B2_G(v2, v6, v10, v14, m[s[4]], m[s[5]]);
+        B2_G(v3, v7, v11, v15, m[s[6]], m[s[7]]);
+        B2_G(v0, v5, v10, v15, m[s[8]], m[s[9]]);
+        B2_G(v1, v6, v11, v12, m[s[10]], m[s[11]]);
+        B2_G(v2, v7, v8, v13, m[s[12]], m[s[13]]);
+        B2_G(v3, v4, v9, v14, m[s[14]], m[s[15]]);
+    }
+    h[0] ^= v0 ^ v8;  h[1] ^= v1 ^ v9;  h[2] ^= v2 ^ v10; h[3] ^= v3 ^ v11;
+    h[4] ^= v4 ^ v12; h[5] ^= v5 ^ v13; h[6] ^= v6 ^ v14; h[7] ^= v7 ^ v15;
+}
+
+__device__ inline void from_state(WState* w, const b2::State* s) {  // requires s->buflen % 8 == 0
+    for (int i = 0; i < 8; i++) w->h[i] = s->h[i];
+    w->t0 = s->t[0];
+    w->nwords = (uint32_t)(s->buflen / 8);
+    for (int i = 0; i < 16; i++) {
+        uint64_t v = 0;
+        for (int j = 7; j >= 0; j--) v = (v << 8) | s->buf[8 * i + j];
+        w->buf[i] = v;
+    }
+}
+__device__ inline void to_state(const WState* w, b2::State* s) {
+    for (int i = 0; i < 8; i++) s->h[i] = w->h[i];
+    s->t[0] = w->t0;
+    s->t[1] = 0;
+    s->buflen = (uint64_t)w->nwords * 8;
+    for (int i = 0; i < 16; i++)
+        for (int j = 0; j < 8; j++) s->buf[8 * i + j] = (i < (int)w->nwords) ? (uint8_t)(w->buf[i] >> (8 * j)) : 0;
+}
+
+static __device__ __noinline__ void absorb_word(WState* w, uint64_t x) {  // Digest::update, one word
+    if (w->nwords == 16) {
+        w->t0 += 128;
+        compress_words(w->h, w->buf, w->t0, false);
+        w->nwords = 0;
+    }
+    w->buf[w->nwords++] = x;
+}
+
+// rng.rs:51-55 + 61-80 for an 8-byte request: out = first word of H(state); then absorb the whole 64-byte digest
+static __device__ __noinline__ uint64_t next_u64(WState* w) {
+    for (int i = 0; i < 8; i++) w->fh[i] = w->h[i];
+    for (int i = 0; i < 16; i++) w->fblk[i] = (i < (int)w->nwords) ? w->buf[i] : 0;
+    compress_words(w->fh, w->fblk, w->t0 + (uint64_t)w->nwords * 8, true);
+    for (int i = 0; i < 8; i++) absorb_word(w, w->fh[i]);
+    return w->fh[0];
+}
+
+// verifier.rs:128-132 -> ark-ff Fp::rand (see b2::sample_fr)
+static __device__ __noinline__ void sample_fr(WState* w, uint64_t out[4]) {
+    const uint64_t P[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
+    for (;;) {
+        for (int i = 0; i < 4; i++) out[i] = next_u64(w);
+        out[3] &= 0x7fffffffffffffffULL;
+        bool lt = false;
+        for (int i = 3; i >= 0; i--) {
+            if (out[i] < P[i]) { lt = true; break; }
+            if (out[i] > P[i]) break;
+        }
+        if (lt) return;
+    }
+}
+
+}  // namespace b2w
+#endif

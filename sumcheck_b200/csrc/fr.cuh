@@ -138,11 +138,8 @@ __device__ __forceinline__ Fr sub(const Fr& a, const Fr& b) {
     return t;
 }
 
-#ifndef FR_MUL_INLINE
-#define FR_MUL_INLINE __forceinline__
-#endif
 // Montgomery product a*b*2^-256 mod p: 63 IMAD.WIDE for the product + 48 for the reduction.
-__device__ FR_MUL_INLINE Fr mul(const Fr& a, const Fr& b) {
+__device__ __forceinline__ Fr mul_impl(const Fr& a, const Fr& b) {
     uint32_t ev[16], od[16];
     mul_wide_eo(ev, od, a.l, b.l);
     uint32_t c = redc_eo(ev, od);
@@ -173,6 +170,16 @@ __device__ FR_MUL_INLINE Fr mul(const Fr& a, const Fr& b) {
 }
 
 
+// FR_COMPACT (latency-bound kernels such as the fused tail): ONE out-of-line copy of the multiplier, arguments by value
+// (registers), so the whole round loop stays resident in the instruction cache instead of streaming ~100 KB of inlined
+// straight-line code per round.  Throughput kernels keep the inlined form.
+#ifdef FR_COMPACT
+static __device__ __noinline__ Fr mul_outlined(Fr a, Fr b) { return mul_impl(a, b); }
+__device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) { return mul_outlined(a, b); }
+#else
+__device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) { return mul_impl(a, b); }
+#endif
+
 // ---- lazily reduced inner products -----------------------------------------------------------------------------
 // A WideAcc holds an UNREDUCED integer sum of Montgomery products x*y (each < p^2 < 2^510) in 17 limbs, so 2^34
 // products can be accumulated before overflow.  One Montgomery reduction at the end turns the whole sum into a field
@@ -188,7 +195,15 @@ __device__ __forceinline__ void wide_zero(WideAcc& w) {
 }
 
 // w += a * b   (integer product, 16 limbs): 64 IMAD.WIDE + 33 carry-chained adds
-__device__ FR_MUL_INLINE void wide_mac(WideAcc& w, const Fr& a, const Fr& b) { wide_mac_limbs(w.l, a.l, b.l); }
+#ifdef FR_COMPACT
+static __device__ __noinline__ WideAcc wide_mac_outlined(WideAcc w, Fr a, Fr b) {
+    wide_mac_limbs(w.l, a.l, b.l);
+    return w;
+}
+__device__ __forceinline__ void wide_mac(WideAcc& w, const Fr& a, const Fr& b) { w = wide_mac_outlined(w, a, b); }
+#else
+__device__ __forceinline__ void wide_mac(WideAcc& w, const Fr& a, const Fr& b) { wide_mac_limbs(w.l, a.l, b.l); }
+#endif
 
 // w += a * 2^256: after the final reduction this contributes exactly `a` (used for single-multiplicand products)
 __device__ __forceinline__ void wide_add_shifted(WideAcc& w, const Fr& a) {
@@ -212,7 +227,11 @@ __device__ __forceinline__ Fr R2() {  // R^2 mod p: mul(x, R2()) = x * R mod p f
 }
 
 // Montgomery-reduce a WideAcc (value V < 2^544) to the canonical field element V * R^-1 mod p.
+#ifdef FR_COMPACT
+static __device__ __noinline__ Fr wide_reduce(WideAcc w) {
+#else
 __device__ __forceinline__ Fr wide_reduce(const WideAcc& w) {
+#endif
     uint32_t ev[17], od[17];
 #pragma unroll
     for (int i = 0; i < 17; i++) { ev[i] = w.l[i]; od[i] = 0; }

@@ -14,6 +14,7 @@
 #pragma once
 #include <cstdint>
 
+#include "blake2b.cuh"
 #include "fr.cuh"
 
 namespace sck {
@@ -43,6 +44,11 @@ struct RoundParams {
     // P(1) from the previous round's claim (rounds >= 2, single launch per round): the launch sums the points
     // t = 0, 2, 3, .., d only (skip1) and, when fix1 is set, the last block fills P(1) = P_prev(r) - P(0).
     uint32_t skip1, fix1, degree;
+    // Result delivery without a copy: when set, the last block also writes the message (Montgomery then canonical,
+    // (d+1)*8 words each) to mapped pinned host memory and then publishes `seq` in *host_flag; the host spins on it.
+    uint32_t* host_out;
+    volatile uint32_t* host_flag;
+    uint32_t seq;
     const uint32_t* prev_evals;     // [(d+1)][8] previous round's ProverMsg (may alias evals_out: read first)
     const uint32_t* lagrange;       // [2][(d+1)][8]: w_j = 1/prod_{k!=j}(j-k), then the field elements 0..d
 };
@@ -121,26 +127,27 @@ __device__ __forceinline__ Fr to_canonical(const Fr& a) {
     return fr::mul(a, one_int);
 }
 
-template <int NPTS, bool FOLD>
-__global__ void __launch_bounds__(128, 3) round_kernel(const RoundParams p) {
-    __shared__ uint32_t s_red[32 * NPTS * 8];
-    __shared__ bool s_last;
-
-    // Per-thread sums are kept UNREDUCED (fr::WideAcc): the last multiply of every product term is a plain 256x256-bit
-    // integer product added into 17 limbs; one Montgomery reduction per evaluation point per thread at the end.
-    fr::WideAcc accw[NPTS];
-#pragma unroll
-    for (int t = 0; t < NPTS; t++) fr::wide_zero(accw[t]);
+// coherent 256-bit load (L2 only): for buffers rewritten by this very kernel (tail_kernel ping-pong)
+__device__ __forceinline__ Fr load_cg(const uint32_t* p) {
     Fr r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.l[i] = p.r[i];
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
 
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+// The hot loop: for every output pair index b = b0, b0+stride, .. < p.n_pairs, (fold and) accumulate the product terms
+// of all evaluation points into the thread's unreduced accumulators.  STREAM selects the read-only streaming loads
+// (tables written by an EARLIER launch) or coherent L2 loads (tables written earlier in the SAME launch).
+template <int NPTS, bool FOLD, bool STREAM>
+__device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const Fr& r, unsigned long long b0, unsigned long long stride,
+                                                 fr::WideAcc (&accw)[NPTS]) {
     const uint32_t row_words = FOLD ? 32u : 16u;  // words of one table consumed per output pair
-    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < p.n_pairs; b += stride) {
+    for (unsigned long long b = b0; b < p.n_pairs; b += stride) {
         // pull the rows of the NEXT grid-stride iteration into L2 now, so their HBM latency overlaps this iteration's
         // ~10^4 cycles of arithmetic and the loads below mostly hit L2
-        if (b + stride < p.n_pairs) {
+        if (STREAM && b + stride < p.n_pairs) {
             for (uint32_t j = 0; j < p.n_tables; j++) {
                 const uint32_t* nxt = p.tab_in[j] + (b + stride) * row_words;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
@@ -155,8 +162,12 @@ __global__ void __launch_bounds__(128, 3) round_kernel(const RoundParams p) {
                 Fr v0, v1;
                 if (FOLD) {
                     const uint32_t* src = tin + b * 32;  // 4 elements x 8 words
-                    Fr e0 = fr::load_stream(src), e1 = fr::load_stream(src + 8), e2 = fr::load_stream(src + 16),
-                       e3 = fr::load_stream(src + 24);
+                    Fr e0, e1, e2, e3;
+                    if (STREAM) {
+                        e0 = fr::load_stream(src); e1 = fr::load_stream(src + 8); e2 = fr::load_stream(src + 16); e3 = fr::load_stream(src + 24);
+                    } else {
+                        e0 = load_cg(src); e1 = load_cg(src + 8); e2 = load_cg(src + 16); e3 = load_cg(src + 24);
+                    }
                     v0 = fr::add(e0, fr::mul(r, fr::sub(e1, e0)));
                     v1 = fr::add(e2, fr::mul(r, fr::sub(e3, e2)));
                     if (p.write_fold && p.prod_first[jj]) {
@@ -214,6 +225,61 @@ __global__ void __launch_bounds__(128, 3) round_kernel(const RoundParams p) {
             }
         }
     }
+}
+
+// Executed by warp 0 (thread 0 holds the NPTS grand totals): deferred coefficient, P(1) from the claim, and the two
+// output forms.  canon_smem (optional): (d+1)*8 words receiving the canonical limbs for an on-device transcript.
+template <int NPTS>
+__device__ __forceinline__ void publish_round(const RoundParams& p, const Fr (&acc)[NPTS], const Fr& r, uint32_t* scratch,
+                                              uint32_t* canon_smem) {
+    Fr claim = fr::zero();
+    if (p.fix1) claim = claim_from_prev(p.prev_evals, p.lagrange, r, p.degree, scratch);  // reads prev before it is overwritten
+    if (threadIdx.x == 0) {
+        Fr c = fr::load(p.coeffs);
+#pragma unroll
+        for (int t = 0; t < NPTS; t++) {
+            Fr v = p.defer_coeff ? fr::mul(acc[t], c) : acc[t];
+            const uint32_t slot = p.skip1 ? (t == 0 ? 0u : (uint32_t)t + 1u) : p.t0 + (uint32_t)t;
+            Fr cv = to_canonical(v);
+            fr::store(p.evals_out + (size_t)slot * 8, v);
+            fr::store(p.canon_out + (size_t)slot * 8, cv);
+            if (canon_smem) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) canon_smem[slot * 8 + i] = cv.l[i];
+            }
+            if (t == 0 && p.skip1) {  // P(1) = claim - P(0); without fix1 (sharded) slot 1 stays zero for the all-gather
+                Fr p1 = p.fix1 ? fr::sub(claim, v) : fr::zero();
+                Fr c1 = to_canonical(p1);
+                fr::store(p.evals_out + 8, p1);
+                fr::store(p.canon_out + 8, c1);
+                if (canon_smem) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) canon_smem[8 + i] = c1.l[i];
+                }
+            }
+        }
+    }
+}
+
+#ifndef SC_MIN_BLOCKS
+#define SC_MIN_BLOCKS 3
+#endif
+template <int NPTS, bool FOLD>
+__global__ void __launch_bounds__(128, SC_MIN_BLOCKS) round_kernel(const RoundParams p) {
+    __shared__ uint32_t s_red[32 * NPTS * 8];
+    __shared__ bool s_last;
+
+    // Per-thread sums are kept UNREDUCED (fr::WideAcc): the last multiply of every product term is a plain 256x256-bit
+    // integer product added into 17 limbs; one Montgomery reduction per evaluation point per thread at the end.
+    fr::WideAcc accw[NPTS];
+#pragma unroll
+    for (int t = 0; t < NPTS; t++) fr::wide_zero(accw[t]);
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = p.r[i];
+
+    accumulate_pairs<NPTS, FOLD, true>(p, r, (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x,
+                                       (unsigned long long)gridDim.x * blockDim.x, accw);
     Fr acc[NPTS];
 #pragma unroll
     for (int t = 0; t < NPTS; t++) acc[t] = fr::wide_reduce(accw[t]);
@@ -240,28 +306,23 @@ __global__ void __launch_bounds__(128, 3) round_kernel(const RoundParams p) {
     }
     block_reduce<NPTS>(acc, s_red);
     if (threadIdx.x >= 32) return;
-    Fr claim = fr::zero();
-    if (p.fix1) claim = claim_from_prev(p.prev_evals, p.lagrange, r, p.degree, s_red);  // reads prev before it is overwritten
+    publish_round<NPTS>(p, acc, r, s_red, nullptr);
     if (threadIdx.x == 0) {
-        Fr c = fr::load(p.coeffs);
-#pragma unroll
-        for (int t = 0; t < NPTS; t++) {
-            Fr v = p.defer_coeff ? fr::mul(acc[t], c) : acc[t];
-            const uint32_t slot = p.skip1 ? (t == 0 ? 0u : (uint32_t)t + 1u) : p.t0 + (uint32_t)t;
-            fr::store(p.evals_out + (size_t)slot * 8, v);
-            fr::store(p.canon_out + (size_t)slot * 8, to_canonical(v));
-            if (t == 0 && p.skip1) {  // P(1) = claim - P(0); without fix1 (sharded) slot 1 stays zero for the all-gather
-                Fr p1 = p.fix1 ? fr::sub(claim, v) : fr::zero();
-                fr::store(p.evals_out + 8, p1);
-                fr::store(p.canon_out + 8, to_canonical(p1));
-            }
-        }
         *p.counter = 0;
+        if (p.host_flag) {  // only the last launch of a round carries a flag; it forwards the whole message
+            const uint32_t n = (p.degree + 1) * 8;
+            for (uint32_t i = 0; i < n; i++) {
+                p.host_out[i] = p.evals_out[i];
+                p.host_out[n + i] = p.canon_out[i];
+            }
+            __threadfence_system();
+            *p.host_flag = p.seq;
+        }
     }
 }
 
 // Lagrange data for claim_from_prev: w_j = 1 / prod_{k != j} (j - k) and the field elements 0..d (one thread per j).
-__global__ void lagrange_setup_kernel(uint32_t d, uint32_t* out) {
+static __global__ void lagrange_setup_kernel(uint32_t d, uint32_t* out) {
     const uint32_t j = threadIdx.x;
     if (j > d) return;
     Fr r2 = {{0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u}};

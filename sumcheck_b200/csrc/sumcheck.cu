@@ -14,6 +14,7 @@
 #include "blake2b.cuh"
 #include "kernels.cuh"
 #include "gkr_kernels.cuh"
+#include "tail_params.cuh"
 
 static_assert(sizeof(sc_blake2b512_rng) == sizeof(b2::State), "sc_blake2b512_rng must be layout-identical to b2::State");
 
@@ -55,6 +56,7 @@ int ensure_device(int device) {
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) return fail(SC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         CUDA_TRY(fr::fr_init_constants());
+        CUDA_TRY(sck::tail_init_constants());
         g_dev[device].sms = prop.multiProcessorCount;
         g_dev[device].ready = true;
     }
@@ -79,7 +81,14 @@ struct sc_prover {
     uint8_t* d_first = nullptr;
     uint32_t *d_partials = nullptr, *d_evals = nullptr, *d_canon = nullptr, *d_lagrange = nullptr;
     unsigned int* d_counter = nullptr;
-    uint32_t *h_evals = nullptr, *h_canon = nullptr;  // pinned
+    uint32_t *h_evals = nullptr, *h_canon = nullptr;  // pinned + mapped: [evals | canon | flag]
+    uint32_t* h_result = nullptr;   // one allocation: (d+1)*8 evals, (d+1)*8 canon, then the flag word
+    uint32_t* d_result = nullptr;   // device alias of h_result
+    uint32_t seq = 0;               // flag value of the last issued round
+    bool want_timing = false;       // record per-round CUDA events (sc_prover_set_timing)
+    // fused tail (device transcript): [nv][d+1][8] evals, [nv][8] challenges, transcript state in/out
+    uint32_t *d_tail_evals = nullptr, *d_tail_chal = nullptr, *h_tail = nullptr;
+    b2::State *d_st = nullptr, *h_st = nullptr;
     int max_grid = 0;
     int cur = 0;  // which buffer holds the current tables: 0 = tab0, 1 = A, 2 = B
     cudaStream_t stream = nullptr;      // the stream work is issued on
@@ -88,6 +97,7 @@ struct sc_prover {
     std::vector<float> round_ms;
     bool timing = false;
     bool used_skip1 = false;  // last device round summed t = 0, 2, .., d only
+    bool direct_results = true;  // single-GPU rounds deliver their message through mapped host memory + flag
     uint64_t launches = 0;
     // where the d+1 results of the last round live on the device (local buffers, the summed copies, or the sub-prover's)
     uint32_t *out_evals = nullptr, *out_canon = nullptr;
@@ -103,10 +113,10 @@ struct sc_prover {
 
 namespace {
 
-template <int NPTS, bool FOLD>
-int occupancy_blocks() {
+template <int NPTS>
+int occupancy_blocks_nofold() {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sck::round_kernel<NPTS, FOLD>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sck::round_kernel<NPTS, false>, 128, 0);
     return nb < 1 ? 1 : nb;
 }
 
@@ -114,16 +124,14 @@ template <int NPTS>
 cudaError_t launch_round(sc_prover* p, bool fold, const sck::RoundParams& rp) {
     const int threads = 128;
     unsigned long long need = (rp.n_pairs + threads - 1) / threads;
-    int occ = fold ? occupancy_blocks<NPTS, true>() : occupancy_blocks<NPTS, false>();
+    int occ = fold ? sck::fold_round_occupancy(NPTS) : occupancy_blocks_nofold<NPTS>();
     unsigned long long cap = (unsigned long long)g_dev[p->device].sms * occ;
     if (cap > (unsigned long long)p->max_grid) cap = p->max_grid;
     int grid = (int)(need < cap ? need : cap);
     if (grid < 1) grid = 1;
-    if (fold)
-        sck::round_kernel<NPTS, true><<<grid, threads, 0, p->stream>>>(rp);
-    else
-        sck::round_kernel<NPTS, false><<<grid, threads, 0, p->stream>>>(rp);
     p->launches++;
+    if (fold) return sck::launch_fold_round(NPTS, grid, rp, p->stream);  // compact translation unit (tail.cu)
+    sck::round_kernel<NPTS, false><<<grid, threads, 0, p->stream>>>(rp);
     return cudaGetLastError();
 }
 
@@ -155,12 +163,18 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
     rp.degree = p->d;
     rp.prev_evals = p->d_evals;
     rp.lagrange = p->d_lagrange;
+    const bool direct = !p->comm && p->direct_results;  // results straight into mapped host memory
+    if (direct) {
+        rp.host_out = p->d_result;
+        rp.seq = ++p->seq;
+    }
     if (fold && p->d <= (uint32_t)sck::MAX_NPTS && p->d_lagrange) {
         // rounds >= 2: P(0) + P(1) = P_prev(r) (the verifier's check, verifier.rs:109), so only t = 0, 2, .., d are summed
         rp.skip1 = 1;
         rp.fix1 = p->comm ? 0u : 1u;  // sharded: the fix needs the GLOBAL P(0) -> done after the all-gather
         rp.t0 = 0;
         rp.write_fold = 1;
+        if (direct) rp.host_flag = p->d_result + (size_t)(p->d + 1) * 16;
         cudaError_t e;
         switch (p->d) {
             case 1: e = launch_round<1>(p, true, rp); break;
@@ -183,6 +197,7 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
         else take = sck::MAX_NPTS;
         rp.t0 = t0;
         rp.write_fold = (t0 == 0) ? 1u : 0u;
+        rp.host_flag = (direct && take == remaining) ? p->d_result + (size_t)(p->d + 1) * 16 : nullptr;
         cudaError_t e;
         switch (take) {
             case 1: e = launch_round<1>(p, fold, rp); break;
@@ -285,8 +300,16 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
         sck::lagrange_setup_kernel<<<1, 32, 0, p->stream>>>(d, p->d_lagrange);
         TRY_P(cudaGetLastError());
     }
-    TRY_P(cudaMallocHost(&p->h_evals, (size_t)(d + 1) * 32));
-    TRY_P(cudaMallocHost(&p->h_canon, (size_t)(d + 1) * 32));
+    TRY_P(cudaHostAlloc(&p->h_result, (size_t)(d + 1) * 64 + 64, cudaHostAllocMapped));
+    memset(p->h_result, 0, (size_t)(d + 1) * 64 + 64);
+    TRY_P(cudaHostGetDevicePointer((void**)&p->d_result, p->h_result, 0));
+    p->h_evals = p->h_result;
+    p->h_canon = p->h_result + (size_t)(d + 1) * 8;
+    TRY_P(cudaMalloc(&p->d_tail_evals, (size_t)nv * (d + 1) * 32));
+    TRY_P(cudaMalloc(&p->d_tail_chal, (size_t)nv * 32));
+    TRY_P(cudaMallocHost(&p->h_tail, (size_t)nv * (d + 2) * 32));
+    TRY_P(cudaMalloc(&p->d_st, 2 * sizeof(b2::State)));
+    TRY_P(cudaMallocHost(&p->h_st, 2 * sizeof(b2::State)));
     p->ev.resize(2 * (size_t)nv);
     for (auto& e : p->ev) TRY_P(cudaEventCreate(&e));
     p->round_ms.assign(nv, 0.f);
@@ -310,7 +333,8 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
     p->round += 1;
     if (p->round > p->nv) return fail(SC_ERR_PANIC_NOT_ACTIVE, "Prover is not active");
     CUDA_TRY(cudaSetDevice(p->device));
-    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1)], p->stream));
+    const bool timed = p->timing && p->want_timing;
+    if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1)], p->stream));
     // prover.rs:85-86: r = randomness[round-1] — the challenge just pushed
     int rc;
     if (p->comm) {
@@ -321,11 +345,98 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
         p->out_canon = p->d_canon;
     }
     if (rc) return rc;
-    if (p->timing) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));
+    if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));
+    if (!p->comm && p->direct_results) {
+        // the last block wrote the message into mapped pinned memory and then the flag: spin instead of copy + sync
+        volatile uint32_t* flag = p->h_result + (size_t)(p->d + 1) * 16;
+        const uint32_t want = p->seq;
+        unsigned long long spins = 0;
+        while (*flag != want) {
+            if ((++spins & 0xfffff) == 0) {  // every ~1M polls make sure the kernel has not died
+                cudaError_t q = cudaStreamQuery(p->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return fail(SC_ERR_CUDA, "round kernel failed: %s", cudaGetErrorString(q));
+                if (q == cudaSuccess && *flag != want) return fail(SC_ERR_CUDA, "round finished without publishing its result");
+            }
+        }
+        __sync_synchronize();
+        return SC_OK;
+    }
     const size_t bytes = (size_t)(p->d + 1) * 32;
     CUDA_TRY(cudaMemcpyAsync(p->h_evals, p->out_evals, bytes, cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaMemcpyAsync(p->h_canon, p->out_canon, bytes, cudaMemcpyDeviceToHost, p->stream));
     if (sync_out) CUDA_TRY(cudaStreamSynchronize(p->stream));
+    return SC_OK;
+}
+
+// First round (1-based) handled by the fused tail kernel, or nv+1 when the tail is not used.
+uint32_t tail_first_round(const sc_prover* p) {
+    // Opt-in (SC_TAIL=1): measured on B200 the single-CTA tail with the device-side Blake2b transcript costs ~60 us per
+    // round against ~36 us for a host-driven round now that results arrive through mapped memory (profiles/README.md).
+    if (p->comm || p->d < 1 || p->d > (uint32_t)sck::MAX_NPTS || !p->d_lagrange || !getenv("SC_TAIL")) return p->nv + 1;
+    for (uint32_t i = 2; i <= p->nv; i++)
+        if (((unsigned long long)1 << (p->nv - i)) <= sck::TAIL_PAIRS) return i;
+    return p->nv + 1;
+}
+
+// Rounds first..nv in ONE launch with the transcript on the device (kernels.cuh tail_kernel).  `r` = challenge drawn
+// after round first-1, `st` = transcript at that point.  Fills evals_out / challenges_out rows first-1 .. nv-1.
+int run_tail(sc_prover* p, b2::State* st, uint32_t first, const uint64_t* r, uint64_t* evals_out, uint64_t* challenges_out) {
+    const uint32_t nv = p->nv, d = p->d, n_rounds = nv - first + 1;
+    CUDA_TRY(cudaSetDevice(p->device));
+    sck::TailParams tp;
+    memset(&tp, 0, sizeof(tp));
+    sck::RoundParams& rp = tp.rp;
+    rp.prod_offsets = p->d_offsets; rp.prod_indices = p->d_indices; rp.prod_first = p->d_first; rp.coeffs = p->d_coeffs;
+    rp.n_products = p->n_products; rp.n_tables = p->T; rp.defer_coeff = (p->n_products == 1) ? 1u : 0u;
+    rp.t0 = 0; rp.write_fold = 1; rp.skip1 = 1; rp.fix1 = 1; rp.degree = d;
+    rp.prev_evals = p->d_evals;  // ProverMsg of round first-1 (host-driven)
+    rp.lagrange = p->d_lagrange;
+    memcpy(rp.r, r, 32);
+    tp.ptrs[0] = p->d_ptr0; tp.ptrs[1] = p->d_ptrA; tp.ptrs[2] = p->d_ptrB;
+    tp.cur = p->cur;
+    tp.n_rounds = n_rounds;
+    tp.n_pairs_first = (unsigned long long)1 << (nv - first);
+    tp.st_in = p->d_st; tp.st_out = p->d_st + 1;
+    tp.evals_all = p->d_tail_evals; tp.chal_all = p->d_tail_chal;
+    long long* d_prof = nullptr;
+    if (getenv("SC_TAIL_PROF")) { CUDA_TRY(cudaMalloc(&d_prof, (size_t)n_rounds * 4 * sizeof(long long))); tp.prof = d_prof; }
+    memcpy(p->h_st, st, sizeof(b2::State));
+    CUDA_TRY(cudaMemcpyAsync(p->d_st, p->h_st, sizeof(b2::State), cudaMemcpyHostToDevice, p->stream));
+    const bool timed = p->timing && p->want_timing;
+    if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (first - 1)], p->stream));
+    CUDA_TRY(sck::launch_tail(d, tp, p->stream));
+    p->launches++;
+    if (timed) {
+        CUDA_TRY(cudaEventRecord(p->ev[2 * (first - 1) + 1], p->stream));
+        for (uint32_t i = first; i < nv; i++) {  // later tail rounds have no launch of their own: zero-length intervals
+            CUDA_TRY(cudaEventRecord(p->ev[2 * i], p->stream));
+            CUDA_TRY(cudaEventRecord(p->ev[2 * i + 1], p->stream));
+        }
+    }
+    const size_t eb = (size_t)n_rounds * (d + 1) * 32, cb = (size_t)n_rounds * 32;
+    CUDA_TRY(cudaMemcpyAsync(p->h_tail, p->d_tail_evals, eb, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaMemcpyAsync((uint8_t*)p->h_tail + eb, p->d_tail_chal, cb, cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaMemcpyAsync(p->h_st + 1, p->d_st + 1, sizeof(b2::State), cudaMemcpyDeviceToHost, p->stream));
+    CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (d_prof) {
+        std::vector<long long> hp((size_t)n_rounds * 4);
+        cudaMemcpy(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        for (uint32_t k = 0; k < n_rounds; k++)
+            fprintf(stderr, "tail round %u: accumulate %lld reduce %lld publish %lld transcript %lld cycles\n", first + k, hp[k * 4], hp[k * 4 + 1], hp[k * 4 + 2], hp[k * 4 + 3]);
+        cudaFree(d_prof);
+    }
+    memcpy(evals_out + (size_t)(first - 1) * (d + 1) * 4, p->h_tail, eb);
+    memcpy(challenges_out + (size_t)(first - 1) * 4, (uint8_t*)p->h_tail + eb, cb);
+    memcpy(st, p->h_st + 1, sizeof(b2::State));
+    // ProverState bookkeeping, as if prove_round had been called for every tail round (prover.rs:82,94)
+    p->randomness.insert(p->randomness.end(), r, r + 4);
+    const uint64_t* ch = challenges_out + (size_t)(first - 1) * 4;
+    p->randomness.insert(p->randomness.end(), ch, ch + (size_t)(n_rounds - 1) * 4);
+    for (uint32_t k = 0; k < n_rounds; k++) p->cur = (p->cur == 1) ? 2 : 1;
+    p->round = nv;
+    // the last tail round's message stays readable through the usual buffers
+    CUDA_TRY(cudaMemcpyAsync(p->d_evals, p->d_tail_evals + (size_t)(n_rounds - 1) * (d + 1) * 8, (size_t)(d + 1) * 32,
+                             cudaMemcpyDeviceToDevice, p->stream));
     return SC_OK;
 }
 
@@ -337,8 +448,14 @@ int run_rounds(sc_prover* p, b2::State* st, uint64_t* evals_out, uint64_t* chall
     b2::put_u64(msg.data(), d + 1);
     uint64_t r[4];
     bool have_r = false;
+    const uint32_t tail_first = tail_first_round(p);
     p->timing = true;
     for (uint32_t i = 0; i < nv; i++) {
+        if (i + 1 == tail_first && have_r && st->buflen % 8 == 0) {
+            int rc = run_tail(p, st, tail_first, r, evals_out, challenges_out);
+            if (rc) { p->timing = false; return rc; }
+            break;
+        }
         int rc = prove_round_impl(p, have_r ? r : nullptr, true);
         if (rc) { p->timing = false; return rc; }
         memcpy(evals_out + (size_t)i * (d + 1) * 4, p->h_evals, (size_t)(d + 1) * 32);
@@ -349,7 +466,10 @@ int run_rounds(sc_prover* p, b2::State* st, uint64_t* evals_out, uint64_t* chall
         memcpy(challenges_out + (size_t)i * 4, r, 32);
     }
     p->timing = false;
-    for (uint32_t i = 0; i < nv; i++) cudaEventElapsedTime(&p->round_ms[i], p->ev[2 * i], p->ev[2 * i + 1]);
+    if (p->want_timing) {
+        cudaStreamSynchronize(p->stream);
+        for (uint32_t i = 0; i < nv; i++) cudaEventElapsedTime(&p->round_ms[i], p->ev[2 * i], p->ev[2 * i + 1]);
+    }
     return SC_OK;
 }
 
@@ -395,8 +515,10 @@ void sc_prover_destroy(sc_prover* p) {
     cudaFree(p->d_ptr0); cudaFree(p->d_ptrA); cudaFree(p->d_ptrB);
     cudaFree(p->d_offsets); cudaFree(p->d_indices); cudaFree(p->d_first); cudaFree(p->d_coeffs);
     cudaFree(p->d_partials); cudaFree(p->d_counter); cudaFree(p->d_evals); cudaFree(p->d_canon); cudaFree(p->d_lagrange);
-    if (p->h_evals) cudaFreeHost(p->h_evals);
-    if (p->h_canon) cudaFreeHost(p->h_canon);
+    cudaFree(p->d_tail_evals); cudaFree(p->d_tail_chal); cudaFree(p->d_st);
+    if (p->h_tail) cudaFreeHost(p->h_tail);
+    if (p->h_st) cudaFreeHost(p->h_st);
+    if (p->h_result) cudaFreeHost(p->h_result);
     for (auto e : p->ev) if (e) cudaEventDestroy(e);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
@@ -528,6 +650,10 @@ uint32_t sc_prover_round_times_ms(const sc_prover* p, float* out, uint32_t cap) 
     return p->nv;
 }
 uint64_t sc_prover_launch_count(const sc_prover* p) { return p->launches; }
+int sc_prover_set_timing(sc_prover* p, int enabled) {
+    p->want_timing = enabled != 0;
+    return SC_OK;
+}
 
 }  // extern "C"
 
