@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(128) to_canonical_kernel(const uint32_t* in, u
 // evals[t] = sum over ranks of gathered[g][t]  (+ canonical form for the transcript); npts <= 32, one warp.
 // fix1: the ranks summed only t = 0, 2, .., d (slot 1 is zero); P(1) = P_prev(r) - P(0) with P_prev = evals_out's old content.
 __global__ void sum_partials_kernel(const uint32_t* gathered, uint32_t n_ranks, uint32_t npts, uint32_t* evals_out, uint32_t* canon_out,
-                                    uint32_t fix1, Fr8 r8, const uint32_t* lagrange) {
+                                    uint32_t fix1, Fr8 r8, const uint32_t* lagrange, uint32_t* host_out,
+                                    volatile uint32_t* host_flag, uint32_t seq) {
     __shared__ uint32_t scratch[32 * 8];
     const uint32_t t = threadIdx.x;
     Fr r, claim = fr::zero();
@@ -155,7 +156,20 @@ __global__ void sum_partials_kernel(const uint32_t* gathered, uint32_t n_ranks, 
         fr::store(evals_out + (size_t)t * 8, acc);
         Fr one_int = fr::zero();
         one_int.l[0] = 1;
-        fr::store(canon_out + (size_t)t * 8, fr::mul(acc, one_int));
+        Fr cv = fr::mul(acc, one_int);
+        fr::store(canon_out + (size_t)t * 8, cv);
+        if (host_out) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                host_out[t * 8 + i] = acc.l[i];
+                host_out[npts * 8 + t * 8 + i] = cv.l[i];
+            }
+        }
+    }
+    if (host_flag) {  // publish after every lane's message words are on their way (mapped pinned memory)
+        __threadfence_system();
+        __syncwarp();
+        if (t == 0) *host_flag = seq;
     }
 }
 // out[j] = tab[j][0] + r * (tab[j][1] - tab[j][0])  for the T two-entry tables of a shard

@@ -49,6 +49,12 @@ struct RoundParams {
     uint32_t* host_out;
     volatile uint32_t* host_flag;
     uint32_t seq;
+    // Multi-GPU: the last block exchanges this rank's NPTS partial sums with every peer through mailboxes in peer
+    // device memory (NVLink stores + a flag), waits for all peers' partials and continues with the global sums —
+    // the collective is fused into the round kernel, no NCCL call and no extra launch (capi_multi.inc).
+    uint32_t* const* peer_mail;     // [n_ranks] mailbox base of every rank as mapped in THIS process; null = single GPU
+    uint32_t n_ranks, rank, mail_slot, mail_seq;
+    uint32_t* comm_error;           // mapped host word set to 1 when a peer does not answer in time
     const uint32_t* prev_evals;     // [(d+1)][8] previous round's ProverMsg (may alias evals_out: read first)
     const uint32_t* lagrange;       // [2][(d+1)][8]: w_j = 1/prod_{k!=j}(j-k), then the field elements 0..d
 };
@@ -264,6 +270,53 @@ __device__ __forceinline__ void publish_round(const RoundParams& p, const Fr (&a
 #ifndef SC_MIN_BLOCKS
 #define SC_MIN_BLOCKS 3
 #endif
+constexpr uint32_t MAIL_WORDS = 64;   // per (slot, rank): up to 6 points x 8 words, flag at word 48
+constexpr uint32_t MAIL_FLAG = 48;
+constexpr uint32_t MAIL_SLOTS = 64;
+
+// Executed by warp 0 of the last block; thread 0 holds this rank's NPTS partial sums.  All-to-all over NVLink peer
+// memory: lane g stores the partials into rank g's mailbox, fences, then raises the flag; lane g then waits for rank
+// g's flag in the local mailbox.  On return thread 0 holds the sums over all ranks (rank order: same on every rank).
+template <int NPTS>
+__device__ __forceinline__ void exchange_partials(const RoundParams& p, Fr (&acc)[NPTS], uint32_t* scratch) {
+    const uint32_t lane = threadIdx.x & 31, G = p.n_ranks;
+    if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < NPTS; t++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) scratch[t * 8 + i] = acc[t].l[i];
+    }
+    __syncwarp();
+    for (uint32_t g = lane; g < G; g += 32) {
+        volatile uint32_t* dst = p.peer_mail[g] + ((size_t)p.mail_slot * G + p.rank) * MAIL_WORDS;
+        for (int w = 0; w < NPTS * 8; w++) dst[w] = scratch[w];
+        __threadfence_system();
+        dst[MAIL_FLAG] = p.mail_seq;
+    }
+    const uint32_t* mine = p.peer_mail[p.rank] + (size_t)p.mail_slot * G * MAIL_WORDS;
+    for (uint32_t g = lane; g < G; g += 32) {
+        const volatile uint32_t* src = mine + (size_t)g * MAIL_WORDS;
+        const long long t0 = clock64();
+        while (src[MAIL_FLAG] != p.mail_seq) {
+            if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer died; report instead of hanging the GPU
+                *p.comm_error = 1;
+                break;
+            }
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < NPTS; t++) {
+            Fr s = fr::zero();
+            for (uint32_t g = 0; g < G; g++) s = fr::add(s, load_cg(mine + (size_t)g * MAIL_WORDS + t * 8));
+            acc[t] = s;
+        }
+    }
+    __syncwarp();
+}
+
 template <int NPTS, bool FOLD>
 __global__ void __launch_bounds__(128, SC_MIN_BLOCKS) round_kernel(const RoundParams p) {
     __shared__ uint32_t s_red[32 * NPTS * 8];
@@ -306,6 +359,7 @@ __global__ void __launch_bounds__(128, SC_MIN_BLOCKS) round_kernel(const RoundPa
     }
     block_reduce<NPTS>(acc, s_red);
     if (threadIdx.x >= 32) return;
+    if (p.peer_mail) exchange_partials<NPTS>(p, acc, s_red);
     publish_round<NPTS>(p, acc, r, s_red, nullptr);
     if (threadIdx.x == 0) {
         *p.counter = 0;

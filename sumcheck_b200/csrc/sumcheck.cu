@@ -97,7 +97,9 @@ struct sc_prover {
     std::vector<float> round_ms;
     bool timing = false;
     bool used_skip1 = false;  // last device round summed t = 0, 2, .., d only
-    bool direct_results = true;  // single-GPU rounds deliver their message through mapped host memory + flag
+    bool direct_results = true;  // rounds deliver their message through mapped host memory + flag
+    bool direct_active = false;  // ... and the round just issued did so
+    bool exchange = false;       // sharded round: fuse the partial-sum exchange into the round kernel
     uint64_t launches = 0;
     // where the d+1 results of the last round live on the device (local buffers, the summed copies, or the sub-prover's)
     uint32_t *out_evals = nullptr, *out_canon = nullptr;
@@ -135,6 +137,9 @@ cudaError_t launch_round(sc_prover* p, bool fold, const sck::RoundParams& rp) {
     return cudaGetLastError();
 }
 
+void set_exchange_params(sc_prover* p, sck::RoundParams& rp);  // capi_multi.inc
+bool comm_failed(const sc_prover* p);
+
 // One protocol round on the device: (fold on r) + sums for all d+1 points.  Results land in d_evals / d_canon.
 int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
     const uint32_t i = p->round;  // already incremented: 1-based round being computed
@@ -163,7 +168,14 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
     rp.degree = p->d;
     rp.prev_evals = p->d_evals;
     rp.lagrange = p->d_lagrange;
-    const bool direct = !p->comm && p->direct_results;  // results straight into mapped host memory
+    const bool direct = (!p->comm || p->exchange) && p->direct_results;  // results straight into mapped host memory
+    p->direct_active = direct;
+    if (p->exchange) {  // sharded + fused exchange: the kernel's outputs are the GLOBAL message; keep it where the NCCL path does
+        set_exchange_params(p, rp);
+        rp.evals_out = p->d_evals_g;
+        rp.canon_out = p->d_canon_g;
+        rp.prev_evals = p->d_evals_g;
+    }
     if (direct) {
         rp.host_out = p->d_result;
         rp.seq = ++p->seq;
@@ -171,7 +183,7 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
     if (fold && p->d <= (uint32_t)sck::MAX_NPTS && p->d_lagrange) {
         // rounds >= 2: P(0) + P(1) = P_prev(r) (the verifier's check, verifier.rs:109), so only t = 0, 2, .., d are summed
         rp.skip1 = 1;
-        rp.fix1 = p->comm ? 0u : 1u;  // sharded: the fix needs the GLOBAL P(0) -> done after the all-gather
+        rp.fix1 = (p->comm && !p->exchange) ? 0u : 1u;  // NCCL path: the fix needs the GLOBAL P(0) -> after the all-gather
         rp.t0 = 0;
         rp.write_fold = 1;
         if (direct) rp.host_flag = p->d_result + (size_t)(p->d + 1) * 16;
@@ -346,7 +358,7 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
     }
     if (rc) return rc;
     if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));
-    if (!p->comm && p->direct_results) {
+    if (p->direct_active) {
         // the last block wrote the message into mapped pinned memory and then the flag: spin instead of copy + sync
         volatile uint32_t* flag = p->h_result + (size_t)(p->d + 1) * 16;
         const uint32_t want = p->seq;
@@ -359,6 +371,7 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
             }
         }
         __sync_synchronize();
+        if (p->comm && comm_failed(p)) return fail(SC_ERR_COMM, "a peer GPU did not deliver its partial sums in time");
         return SC_OK;
     }
     const size_t bytes = (size_t)(p->d + 1) * 32;

@@ -168,6 +168,20 @@ def test_generic_feedable_rng_path(orc):
     assert np.array_equal(np.stack([m.evaluations for m in proof]), evals)
 
 
+@pytest.mark.parametrize("nv,n_products,m,pre", [(3, 1, 3, b""), (11, 1, 3, b""), (12, 1, 2, b"12345678"), (13, 2, 2, b""),
+                                                  (14, 1, 5, b"x" * 24), (12, 1, 1, b""), (12, 1, 3, b"Test Trivial Works")])
+def test_fused_tail_device_transcript(orc, monkeypatch, nv, n_products, m, pre):
+    """SC_TAIL=1: the last rounds run in ONE launch with the Blake2b transcript on the device.  An
+    18-byte pre-feed leaves the hash buffer unaligned, which must silently keep the host transcript."""
+    monkeypatch.setenv("SC_TAIL", "1")
+    T = n_products * m
+    tabs = [orc.synth_table(1 << nv, 4200 + 10 * nv + j) for j in range(T)]
+    coeffs = orc.synth_table(n_products, 4299 + nv)
+    prods = [(coeffs[k], list(range(k * m, (k + 1) * m))) for k in range(n_products)]
+    opoly = orc.Poly(nv, tabs, prods)
+    assert_same_proof(orc, build_poly(nv, opoly.tables, prods), opoly, pre_feed=pre)
+
+
 def test_reset_reproves_identically(orc):
     nv = 10
     tabs = [orc.synth_table(1 << nv, 900 + j) for j in range(3)]

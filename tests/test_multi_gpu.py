@@ -22,7 +22,7 @@ def _worker(rank, world, port, q):
         from sumcheck_b200 import multi
         comm = multi.Comm(multi.broadcast_unique_id(dist, rank), rank, world, rank)
         results = []
-        for nv, n_products, m, seed in [(world.bit_length(), 1, 2, 4), (6, 1, 3, 1), (9, 2, 2, 2), (12, 3, 4, 3), (16, 1, 3, 5)]:
+        for nv, n_products, m, seed in [(world.bit_length(), 1, 2, 4), (6, 1, 3, 1), (9, 2, 2, 2), (12, 3, 4, 3), (16, 1, 3, 5), (10, 1, 5, 6), (9, 1, 7, 7)]:
             T = n_products * m
             tabs = [orc.synth_table(1 << nv, seed * 100 + j) for j in range(T)]
             coeffs = orc.synth_table(n_products, seed * 100 + 99)
