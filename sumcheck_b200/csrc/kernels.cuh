@@ -234,36 +234,64 @@ __device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const Fr&
 }
 
 // Executed by warp 0 (thread 0 holds the NPTS grand totals): deferred coefficient, P(1) from the claim, and the two
-// output forms.  canon_smem (optional): (d+1)*8 words receiving the canonical limbs for an on-device transcript.
+// output forms.  The d+1 output slots are spread over the lanes (each needs a coefficient multiply and a
+// Montgomery->canonical multiply) so a latency-bound small round pays two multiplies, not 2(d+1).
+// canon_smem (optional): (d+1)*8 words receiving the canonical limbs for an on-device transcript.
 template <int NPTS>
 __device__ __forceinline__ void publish_round(const RoundParams& p, const Fr (&acc)[NPTS], const Fr& r, uint32_t* scratch,
                                               uint32_t* canon_smem) {
+    const uint32_t lane = threadIdx.x & 31;
     Fr claim = fr::zero();
     if (p.fix1) claim = claim_from_prev(p.prev_evals, p.lagrange, r, p.degree, scratch);  // reads prev before it is overwritten
-    if (threadIdx.x == 0) {
-        Fr c = fr::load(p.coeffs);
+    // hand the totals (and the claim) to the lanes through shared memory
+    if (lane == 0) {
 #pragma unroll
-        for (int t = 0; t < NPTS; t++) {
-            Fr v = p.defer_coeff ? fr::mul(acc[t], c) : acc[t];
-            const uint32_t slot = p.skip1 ? (t == 0 ? 0u : (uint32_t)t + 1u) : p.t0 + (uint32_t)t;
-            Fr cv = to_canonical(v);
-            fr::store(p.evals_out + (size_t)slot * 8, v);
-            fr::store(p.canon_out + (size_t)slot * 8, cv);
-            if (canon_smem) {
+        for (int t = 0; t < NPTS; t++)
 #pragma unroll
-                for (int i = 0; i < 8; i++) canon_smem[slot * 8 + i] = cv.l[i];
-            }
-            if (t == 0 && p.skip1) {  // P(1) = claim - P(0); without fix1 (sharded) slot 1 stays zero for the all-gather
-                Fr p1 = p.fix1 ? fr::sub(claim, v) : fr::zero();
-                Fr c1 = to_canonical(p1);
-                fr::store(p.evals_out + 8, p1);
-                fr::store(p.canon_out + 8, c1);
-                if (canon_smem) {
+            for (int i = 0; i < 8; i++) scratch[t * 8 + i] = acc[t].l[i];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) canon_smem[8 + i] = c1.l[i];
-                }
+        for (int i = 0; i < 8; i++) scratch[NPTS * 8 + i] = claim.l[i];
+    }
+    __syncwarp();
+    // lane s < NPTS owns summed point s; with skip1 lane NPTS owns P(1) = claim - P(0)
+    const bool owner = lane < (uint32_t)NPTS, fixer = p.skip1 && lane == (uint32_t)NPTS;
+    if (owner || fixer) {
+        Fr v;
+        const uint32_t src = owner ? lane : 0u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) v.l[i] = scratch[src * 8 + i];
+        if (p.defer_coeff) v = fr::mul(v, fr::load(p.coeffs));
+        uint32_t slot = p.skip1 ? (lane == 0 ? 0u : lane + 1u) : p.t0 + lane;
+        if (fixer) {
+            slot = 1;
+            if (p.fix1) {
+                Fr cl;
+#pragma unroll
+                for (int i = 0; i < 8; i++) cl.l[i] = scratch[NPTS * 8 + i];
+                v = fr::sub(cl, v);
+            } else {
+                v = fr::zero();  // sharded NCCL path: slot 1 stays zero for the all-gather
             }
         }
+        const Fr cv = to_canonical(v);
+        fr::store(p.evals_out + (size_t)slot * 8, v);
+        if (p.canon_out) fr::store(p.canon_out + (size_t)slot * 8, cv);
+        if (canon_smem) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) canon_smem[slot * 8 + i] = cv.l[i];
+        }
+        if (p.host_out) {  // mapped pinned host memory: Montgomery words, then canonical words
+            const uint32_t n = (p.degree + 1) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                p.host_out[slot * 8 + i] = v.l[i];
+                p.host_out[n + slot * 8 + i] = cv.l[i];
+            }
+        }
+    }
+    if (p.host_flag) {
+        __threadfence_system();
+        __syncwarp();
     }
 }
 
@@ -338,41 +366,32 @@ __global__ void __launch_bounds__(128, SC_MIN_BLOCKS) round_kernel(const RoundPa
     for (int t = 0; t < NPTS; t++) acc[t] = fr::wide_reduce(accw[t]);
 
     block_reduce<NPTS>(acc, s_red);
-    if (threadIdx.x == 0) {
+    if (gridDim.x > 1) {  // a single-CTA launch (small rounds) already holds the grand totals in thread 0
+        if (threadIdx.x == 0) {
 #pragma unroll
-        for (int t = 0; t < NPTS; t++) fr::store(p.partials + ((size_t)blockIdx.x * NPTS + t) * 8, acc[t]);
+            for (int t = 0; t < NPTS; t++) fr::store(p.partials + ((size_t)blockIdx.x * NPTS + t) * 8, acc[t]);
+            __threadfence();
+            unsigned int ticket = atomicAdd(p.counter, 1u);
+            s_last = (ticket == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (!s_last) return;
+        // Last block to finish: sum the per-block partials (prover.rs:138-148, the rayon reduce)
         __threadfence();
-        unsigned int ticket = atomicAdd(p.counter, 1u);
-        s_last = (ticket == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!s_last) return;
-
-    // Last block to finish: sum the per-block partials (prover.rs:138-148, the rayon reduce), apply the deferred
-    // coefficient, publish P(t0..t0+NPTS-1).
-    __threadfence();
 #pragma unroll
-    for (int t = 0; t < NPTS; t++) acc[t] = fr::zero();
-    for (uint32_t g = threadIdx.x; g < gridDim.x; g += blockDim.x) {
+        for (int t = 0; t < NPTS; t++) acc[t] = fr::zero();
+        for (uint32_t g = threadIdx.x; g < gridDim.x; g += blockDim.x) {
 #pragma unroll
-        for (int t = 0; t < NPTS; t++) acc[t] = fr::add(acc[t], fr::load(p.partials + ((size_t)g * NPTS + t) * 8));
+            for (int t = 0; t < NPTS; t++) acc[t] = fr::add(acc[t], fr::load(p.partials + ((size_t)g * NPTS + t) * 8));
+        }
+        block_reduce<NPTS>(acc, s_red);
+        if (threadIdx.x == 0) *p.counter = 0;
     }
-    block_reduce<NPTS>(acc, s_red);
     if (threadIdx.x >= 32) return;
     if (p.peer_mail) exchange_partials<NPTS>(p, acc, s_red);
+    // deferred coefficient, P(1) from the claim, both output forms; with a flag the message also goes to mapped host memory
     publish_round<NPTS>(p, acc, r, s_red, nullptr);
-    if (threadIdx.x == 0) {
-        *p.counter = 0;
-        if (p.host_flag) {  // only the last launch of a round carries a flag; it forwards the whole message
-            const uint32_t n = (p.degree + 1) * 8;
-            for (uint32_t i = 0; i < n; i++) {
-                p.host_out[i] = p.evals_out[i];
-                p.host_out[n + i] = p.canon_out[i];
-            }
-            __threadfence_system();
-            *p.host_flag = p.seq;
-        }
-    }
+    if (threadIdx.x == 0 && p.host_flag) *p.host_flag = p.seq;
 }
 
 // Lagrange data for claim_from_prev: w_j = 1 / prod_{k != j} (j - k) and the field elements 0..d (one thread per j).

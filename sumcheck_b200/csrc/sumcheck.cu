@@ -210,6 +210,7 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
         rp.t0 = t0;
         rp.write_fold = (t0 == 0) ? 1u : 0u;
         rp.host_flag = (direct && take == remaining) ? p->d_result + (size_t)(p->d + 1) * 16 : nullptr;
+        rp.host_out = direct ? p->d_result : nullptr;
         cudaError_t e;
         switch (take) {
             case 1: e = launch_round<1>(p, fold, rp); break;
