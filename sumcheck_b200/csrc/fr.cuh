@@ -180,6 +180,62 @@ __device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) { return mul_outline
 __device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) { return mul_impl(a, b); }
 #endif
 
+// ---- multiplication by the round's challenge (the fix_variables fold) --------------------------------------------
+// Every fold of a round multiplies by the SAME r, so r is expanded once per round into eight plain-integer constants
+// C[k] = r * 2^(32k+64) mod p (k = 0..7).  For a Montgomery-form d,  V = sum_k d.l[k] * C[k]  is 64 wide MACs whose rows
+// all land on limb 0, V == r*d*2^64 (mod p), V < 2^290; a 2-digit Montgomery reduction (12 wide MACs) then gives
+// r*d mod p < 2p.  76 IMAD.WIDE instead of 111 for the general product — and r no longer occupies 8 registers.
+__device__ __forceinline__ Fr fold_const(const Fr& r_mont, int k) {
+    // X_k = 2^(32k+64) mod p as a raw integer; mul(r_mont, X_k) = r * X_k mod p (r = the challenge's canonical value)
+    Fr x = zero();
+    if (k < 6) {
+        x.l[k + 2] = 1;
+    } else if (k == 6) {
+        x = one();  // 2^256 mod p
+    } else {
+        Fr x7 = {{0xcaaf6b13u, 0x355094eau, 0x69a568efu, 0xf6b10cb3u, 0x40cc3869u, 0xe2c926a6u, 0xed269aadu, 0x736a6d3bu}};  // 2^288 mod p
+        x = x7;
+    }
+    return mul(r_mont, x);
+}
+
+// r * d (Montgomery form in, Montgomery form out), C = the 8 x 8 limbs written by fold_const (shared memory)
+__device__ __forceinline__ Fr mul_round_const(const uint32_t* C, const Fr& d) {
+    uint32_t ev[10], od[10];
+    mulc_rows_eo(ev, od, C, d.l);
+    uint32_t c = redc2_eo10(ev, od);
+    // quotient limbs j = 0..7: ev[2+j] + od[1+j] (+ c at j = 0); it is < 2p, so od[9] and the carry out are zero
+    Fr t;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;\n\t"
+        : "=r"(t.l[0]), "=r"(t.l[1]), "=r"(t.l[2]), "=r"(t.l[3]), "=r"(t.l[4]), "=r"(t.l[5]), "=r"(t.l[6]), "=r"(t.l[7])
+        : "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(ev[9]), "r"(od[1]),
+          "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]));
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.u32 %7, %7, 0;\n\t"
+        : "+r"(t.l[0]), "+r"(t.l[1]), "+r"(t.l[2]), "+r"(t.l[3]), "+r"(t.l[4]), "+r"(t.l[5]), "+r"(t.l[6]), "+r"(t.l[7])
+        : "r"(c));
+    return reduce_once(t);
+}
+#ifdef FR_COMPACT
+static __device__ __noinline__ Fr mul_round_const_outlined(const uint32_t* C, Fr d) { return mul_round_const(C, d); }
+#define FR_MUL_ROUND_CONST(C, d) fr::mul_round_const_outlined(C, d)
+#else
+#define FR_MUL_ROUND_CONST(C, d) fr::mul_round_const(C, d)
+#endif
+
 // ---- lazily reduced inner products -----------------------------------------------------------------------------
 // A WideAcc holds an UNREDUCED integer sum of Montgomery products x*y (each < p^2 < 2^510) in 17 limbs, so 2^34
 // products can be accumulated before overflow.  One Montgomery reduction at the end turns the whole sum into a field

@@ -155,10 +155,10 @@ emit("")
 
 # ---- Montgomery reduction, 32-bit digits.  -p^-1 mod 2^32 = 0xffffffff so m_i = -S_i; p[0] = 1 so the digit-0 product is
 # folded into the carry c_{i+1} = (S_i + m_i) >> 32 and never issued.
-for top, name in ((15, "redc_eo"), (16, "redc_eo17")):
+for top, name, ndig in ((15, "redc_eo", 8), (16, "redc_eo17", 8), (9, "redc2_eo10", 2)):
     n = top + 1
-    emit(f"// In place: (EV + OD*2^32) += M*p with M chosen so the low 256 bits vanish; returns the carry into limb 8.")
-    emit(f"// Afterwards limbs 8..{top} of EV and 7..{top - 1} of OD hold the (unmerged) quotient.")
+    emit(f"// In place: (EV + OD*2^32) += M*p with M chosen so the low {32 * ndig} bits vanish; returns the carry into limb {ndig}.")
+    emit(f"// Afterwards limbs {ndig}..{top} of EV and {ndig - 1}..{top - 1} of OD hold the (unmerged) quotient.")
     emit(f"__device__ __forceinline__ uint32_t {name}(uint32_t (&ev)[{n}], uint32_t (&od)[{n}]) {{")
     emit("    uint32_t c = 0, m, s, k1, k2, nz, h1;")
     emit("    uint32_t pc[8];  // modulus limbs from constant memory: register/uniform operands keep the IMAD.WIDE fusion")
@@ -167,7 +167,7 @@ for top, name in ((15, "redc_eo"), (16, "redc_eo17")):
     emit("    // m = -S must not LOOK like a negation: ptxas folds `0 - s` into the multiply as a negated operand, which")
     emit("    // un-fuses every IMAD.WIDE of the chain into IMAD + IMAD.HI.  Subtracting from a zero it cannot see avoids that.")
     emit("    const uint32_t zero = FR_MODULUS[8];")
-    for i in range(8):
+    for i in range(ndig):
         prev = f"od[{i - 1}]" if i > 0 else "0u"
         emit(f"    // digit {i}: S = ev[{i}] + {prev} + c")
         emit(f"    s = ev[{i}] + {prev}; k1 = (s < ev[{i}]) ? 1u : 0u; s += c; k2 = (s < c) ? 1u : 0u;")
@@ -186,6 +186,25 @@ for top, name in ((15, "redc_eo"), (16, "redc_eo17")):
     emit("")
 
 
+
+# ---- multiplication by a per-round constant (the fold): V = sum_k d[k] * C[k], all rows land on limb 0.
+emit("// ev/od (10 limbs) = sum_k d[k] * C[k] where C[k] (8 limbs each, shared memory, warp-uniform) are the per-round")
+emit("// constants r * 2^(32k+64) mod p: then V == r * d * 2^64 (mod p) with V < 2^290, and a TWO-digit Montgomery")
+emit("// reduction (redc2_eo10) brings it to r*d mod p — 64 + 12 IMAD.WIDE instead of 63 + 48 for a general product.")
+emit("__device__ __forceinline__ void mulc_rows_eo(uint32_t (&ev)[10], uint32_t (&od)[10], const uint32_t* C, const uint32_t (&d)[8]) {")
+emit("    uint32_t c[8];")
+for k in range(8):
+    emit(f"    {{ const uint4 lo = *reinterpret_cast<const uint4*>(C + {8 * k}), hi = *reinterpret_cast<const uint4*>(C + {8 * k + 4});")
+    emit("      c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w; c[4] = hi.x; c[5] = hi.y; c[6] = hi.z; c[7] = hi.w; }")
+    if k == 0:
+        chain("ev", 0, 4, ["c[0]", "c[2]", "c[4]", "c[6]"], "d[0]", -1, first_is_mul=True)
+        chain("od", 0, 4, ["c[1]", "c[3]", "c[5]", "c[7]"], "d[0]", -1, first_is_mul=True)
+        emit("    ev[8] = 0; ev[9] = 0; od[8] = 0; od[9] = 0;")
+    else:
+        chain("ev", 0, 4, ["c[0]", "c[2]", "c[4]", "c[6]"], f"d[{k}]", 9)
+        chain("od", 0, 4, ["c[1]", "c[3]", "c[5]", "c[7]"], f"d[{k}]", 9)
+emit("}")
+emit("")
 emit("// w[0..16] += EV + OD*2^32 where (ev, od) = a*b: the merge of the two accumulators and the accumulation in two")
 emit("// split carry chains each (asm statements are limited to 30 operands).")
 emit("__device__ __forceinline__ void wide_mac_limbs(uint32_t (&w)[17], const uint32_t (&a)[8], const uint32_t (&b)[8]) {")

@@ -146,9 +146,19 @@ __device__ __forceinline__ Fr load_cg(const uint32_t* p) {
 // The hot loop: for every output pair index b = b0, b0+stride, .. < p.n_pairs, (fold and) accumulate the product terms
 // of all evaluation points into the thread's unreduced accumulators.  STREAM selects the read-only streaming loads
 // (tables written by an EARLIER launch) or coherent L2 loads (tables written earlier in the SAME launch).
+// Expand the round's challenge into the fold constants (fr.cuh fold_const) in shared memory: threads 0..7, one each.
+__device__ __forceinline__ void prepare_fold_consts(const Fr& r, uint32_t* foldC /* [8][8] */) {
+    if (threadIdx.x < 8) {
+        Fr c = fr::fold_const(r, (int)threadIdx.x);
+#pragma unroll
+        for (int i = 0; i < 8; i++) foldC[threadIdx.x * 8 + i] = c.l[i];
+    }
+    __syncthreads();
+}
+
 template <int NPTS, bool FOLD, bool STREAM>
-__device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const Fr& r, unsigned long long b0, unsigned long long stride,
-                                                 fr::WideAcc (&accw)[NPTS]) {
+__device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const uint32_t* foldC, unsigned long long b0,
+                                                 unsigned long long stride, fr::WideAcc (&accw)[NPTS]) {
     const uint32_t row_words = FOLD ? 32u : 16u;  // words of one table consumed per output pair
     for (unsigned long long b = b0; b < p.n_pairs; b += stride) {
         // pull the rows of the NEXT grid-stride iteration into L2 now, so their HBM latency overlaps this iteration's
@@ -174,8 +184,8 @@ __device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const Fr&
                     } else {
                         e0 = load_cg(src); e1 = load_cg(src + 8); e2 = load_cg(src + 16); e3 = load_cg(src + 24);
                     }
-                    v0 = fr::add(e0, fr::mul(r, fr::sub(e1, e0)));
-                    v1 = fr::add(e2, fr::mul(r, fr::sub(e3, e2)));
+                    v0 = fr::add(e0, FR_MUL_ROUND_CONST(foldC, fr::sub(e1, e0)));
+                    v1 = fr::add(e2, FR_MUL_ROUND_CONST(foldC, fr::sub(e3, e2)));
                     if (p.write_fold && p.prod_first[jj]) {
                         uint32_t* dst = p.tab_out[idx] + b * 16;
                         fr::store(dst, v0);
@@ -355,11 +365,13 @@ __global__ void __launch_bounds__(128, SC_MIN_BLOCKS) round_kernel(const RoundPa
     fr::WideAcc accw[NPTS];
 #pragma unroll
     for (int t = 0; t < NPTS; t++) fr::wide_zero(accw[t]);
+    __shared__ __align__(16) uint32_t s_foldC[64];
     Fr r;
 #pragma unroll
     for (int i = 0; i < 8; i++) r.l[i] = p.r[i];
+    if (FOLD) prepare_fold_consts(r, s_foldC);
 
-    accumulate_pairs<NPTS, FOLD, true>(p, r, (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x,
+    accumulate_pairs<NPTS, FOLD, true>(p, s_foldC, (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x,
                                        (unsigned long long)gridDim.x * blockDim.x, accw);
     Fr acc[NPTS];
 #pragma unroll

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(const TailParams 
     __shared__ uint32_t s_canon[(MAX_NPTS + 1) * 8];
     __shared__ uint32_t s_r[8];
     __shared__ b2w::WState s_ws;
+    __shared__ __align__(16) uint32_t s_foldC[64];
     const uint32_t npts_msg = tp.rp.degree + 1;
     if (threadIdx.x == 0) b2w::from_state(&s_ws, tp.st_in);
     Fr r;
@@ -64,10 +65,11 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) tail_kernel(const TailParams 
 #pragma unroll
         for (int t = 0; t < NPTS; t++) fr::wide_zero(accw[t]);
         // the first tail round reads tables written by an earlier launch; later ones read what this CTA just wrote
+        prepare_fold_consts(r, s_foldC);
         if (rd == 0)
-            accumulate_pairs<NPTS, true, true>(p, r, threadIdx.x, blockDim.x, accw);
+            accumulate_pairs<NPTS, true, true>(p, s_foldC, threadIdx.x, blockDim.x, accw);
         else
-            accumulate_pairs<NPTS, true, false>(p, r, threadIdx.x, blockDim.x, accw);
+            accumulate_pairs<NPTS, true, false>(p, s_foldC, threadIdx.x, blockDim.x, accw);
         tk1 = clock64();
         Fr acc[NPTS];
 #pragma unroll
