@@ -159,16 +159,7 @@ __device__ __forceinline__ void prepare_fold_consts(const Fr& r, uint32_t* foldC
 template <int NPTS, bool FOLD, bool STREAM>
 __device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const uint32_t* foldC, unsigned long long b0,
                                                  unsigned long long stride, fr::WideAcc (&accw)[NPTS]) {
-    const uint32_t row_words = FOLD ? 32u : 16u;  // words of one table consumed per output pair
     for (unsigned long long b = b0; b < p.n_pairs; b += stride) {
-        // pull the rows of the NEXT grid-stride iteration into L2 now, so their HBM latency overlaps this iteration's
-        // ~10^4 cycles of arithmetic and the loads below mostly hit L2
-        if (STREAM && b + stride < p.n_pairs) {
-            for (uint32_t j = 0; j < p.n_tables; j++) {
-                const uint32_t* nxt = p.tab_in[j] + (b + stride) * row_words;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
-            }
-        }
         for (uint32_t k = 0; k < p.n_products; k++) {
             Fr prod[NPTS];
             const uint32_t j0 = p.prod_offsets[k], j1 = p.prod_offsets[k + 1];
@@ -308,6 +299,10 @@ __device__ __forceinline__ void publish_round(const RoundParams& p, const Fr (&a
 #ifndef SC_MIN_BLOCKS
 #define SC_MIN_BLOCKS 3
 #endif
+#ifndef SC_THREADS
+#define SC_THREADS 128
+#endif
+constexpr int ROUND_THREADS = SC_THREADS;  // CTA size of round_kernel in this translation unit
 constexpr uint32_t MAIL_WORDS = 64;   // per (slot, rank): up to 6 points x 8 words, flag at word 48
 constexpr uint32_t MAIL_FLAG = 48;
 constexpr uint32_t MAIL_SLOTS = 64;
@@ -356,7 +351,7 @@ __device__ __forceinline__ void exchange_partials(const RoundParams& p, Fr (&acc
 }
 
 template <int NPTS, bool FOLD>
-__global__ void __launch_bounds__(128, SC_MIN_BLOCKS) round_kernel(const RoundParams p) {
+__global__ void __launch_bounds__(SC_THREADS, SC_MIN_BLOCKS) round_kernel(const RoundParams p) {
     __shared__ uint32_t s_red[32 * NPTS * 8];
     __shared__ bool s_last;
 

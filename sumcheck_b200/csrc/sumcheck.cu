@@ -118,13 +118,13 @@ namespace {
 template <int NPTS>
 int occupancy_blocks_nofold() {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sck::round_kernel<NPTS, false>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sck::round_kernel<NPTS, false>, sck::ROUND_THREADS, 0);
     return nb < 1 ? 1 : nb;
 }
 
 template <int NPTS>
 cudaError_t launch_round(sc_prover* p, bool fold, const sck::RoundParams& rp) {
-    const int threads = 128;
+    const int threads = fold ? sck::fold_round_threads() : sck::ROUND_THREADS;
     unsigned long long need = (rp.n_pairs + threads - 1) / threads;
     int occ = fold ? sck::fold_round_occupancy(NPTS) : occupancy_blocks_nofold<NPTS>();
     unsigned long long cap = (unsigned long long)g_dev[p->device].sms * occ;
@@ -302,7 +302,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     TRY_P(cudaMemcpyAsync(p->d_indices, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
     TRY_P(cudaMemcpyAsync(p->d_first, first.data(), nnz, cudaMemcpyHostToDevice, p->stream));
     TRY_P(cudaMemcpyAsync(p->d_coeffs, coeffs, (size_t)n_products * 32, cudaMemcpyHostToDevice, p->stream));
-    p->max_grid = g_dev[device].sms * 16;
+    p->max_grid = g_dev[device].sms * 32;
     TRY_P(cudaMalloc(&p->d_partials, (size_t)p->max_grid * sck::MAX_NPTS * 32));
     TRY_P(cudaMalloc(&p->d_counter, sizeof(unsigned int)));
     TRY_P(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned int), p->stream));

@@ -13,25 +13,27 @@ cudaError_t tail_init_constants() { return fr::fr_init_constants(); }  // this T
 // Fold rounds (FOLD = true) are also launched from this compact translation unit: measured on B200 the out-of-line
 // multiplier makes rounds >= 2 3-15 % faster (smaller code, no instruction-fetch stalls), while round 1 (no fold, pure
 // streaming multiply-reduce) is 10 % faster fully inlined and stays in sumcheck.cu.
+int fold_round_threads() { return ROUND_THREADS; }
+
 int fold_round_occupancy(uint32_t npts) {
     int nb = 0;
     switch (npts) {
-        case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<1, true>, 128, 0); break;
-        case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<2, true>, 128, 0); break;
-        case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<3, true>, 128, 0); break;
-        case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<4, true>, 128, 0); break;
-        default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<5, true>, 128, 0); break;
+        case 1: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<1, true>, ROUND_THREADS, 0); break;
+        case 2: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<2, true>, ROUND_THREADS, 0); break;
+        case 3: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<3, true>, ROUND_THREADS, 0); break;
+        case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<4, true>, ROUND_THREADS, 0); break;
+        default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, round_kernel<5, true>, ROUND_THREADS, 0); break;
     }
     return nb < 1 ? 1 : nb;
 }
 
 cudaError_t launch_fold_round(uint32_t npts, int grid, const RoundParams& rp, cudaStream_t stream) {
     switch (npts) {
-        case 1: round_kernel<1, true><<<grid, 128, 0, stream>>>(rp); break;
-        case 2: round_kernel<2, true><<<grid, 128, 0, stream>>>(rp); break;
-        case 3: round_kernel<3, true><<<grid, 128, 0, stream>>>(rp); break;
-        case 4: round_kernel<4, true><<<grid, 128, 0, stream>>>(rp); break;
-        case 5: round_kernel<5, true><<<grid, 128, 0, stream>>>(rp); break;
+        case 1: round_kernel<1, true><<<grid, ROUND_THREADS, 0, stream>>>(rp); break;
+        case 2: round_kernel<2, true><<<grid, ROUND_THREADS, 0, stream>>>(rp); break;
+        case 3: round_kernel<3, true><<<grid, ROUND_THREADS, 0, stream>>>(rp); break;
+        case 4: round_kernel<4, true><<<grid, ROUND_THREADS, 0, stream>>>(rp); break;
+        case 5: round_kernel<5, true><<<grid, ROUND_THREADS, 0, stream>>>(rp); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

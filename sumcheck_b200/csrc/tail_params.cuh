@@ -23,6 +23,7 @@ struct TailParams {
 
 cudaError_t tail_init_constants();
 int fold_round_occupancy(uint32_t npts);
+int fold_round_threads();
 cudaError_t launch_fold_round(uint32_t npts, int grid, const RoundParams& rp, cudaStream_t stream);
 cudaError_t launch_tail(uint32_t degree, const TailParams& tp, cudaStream_t stream);
 

@@ -157,11 +157,11 @@ def bench_main(args, nv, d, T, METRIC, UNIT, field_sums, algorithmic_bytes, Cloc
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32x8 Montgomery (mod p, 255-bit)", "data": "synthetic",
             "config": {"workload": f"MLSumcheck prove nv={nv} deg={d} T={T}, 1 product (BASELINE config 3), tables sharded by the high "
-                                   f"{world.bit_length() - 1} hypercube bits over {world} GPUs, per-round all-gather of the d+1 partial sums",
+                                   f"{world.bit_length() - 1} hypercube bits over {world} GPUs, per-round exchange of the d+1 partial sums fused into the round kernel (NVLink peer memory)",
                        "cache": f"per-GPU shard {T * n_loc * 32 / 2**20:.0f} MiB, re-read from HBM every step",
                        "round_ms_rank0": [round(float(x), 4) for x in round_ms], "ranks_agree": bool(agree.item())},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "kernel": "sck::round_kernel<4,true> on rank 0's shard (incl. the per-round exchange), sharded rounds aggregated",
+                         "kernel": "sck::round_kernel<3,true> on rank 0's shard (incl. the fused peer-memory exchange), sharded rounds aggregated",
                          "peak_source": src},
             "e2e": {"value": fs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": T * n_loc * 32 * world,
                     "d2h_bytes_per_step": nv * (d + 1) * 32 * 2 * world, "ms_per_step": ms_e2e},
