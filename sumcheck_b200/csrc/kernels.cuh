@@ -222,10 +222,28 @@ __device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const uin
                         SC_NEXT_POINT(t)
                     }
                 } else {
+                    // After k multiplicands prod[.] is a degree-k polynomial in the evaluation point, so on consecutive
+                    // points only k+1 values need a multiply; the others follow by finite differences (integer
+                    // combinations, exact): k = 2: q(t) = 3(q(t-1) - q(t-2)) + q(t-3);  k = 3: q(t) = 4(q(t-1) + q(t-3)) -
+                    // 6 q(t-2) - q(t-4).  Saves one of the four multiplies of round 1 at degree 3.
+                    const uint32_t kdeg = jj - j0 + 1;
+                    const bool consecutive = !p.skip1;
 #pragma unroll
                     for (int t = 0; t < NPTS; t++) {
-                        prod[t] = fr::mul(prod[t], cur);
-                        SC_NEXT_POINT(t)
+                        if (t >= 3 && consecutive && kdeg == 2) {
+                            Fr dd = fr::sub(prod[t - 1], prod[t - 2]);
+                            prod[t] = fr::add(fr::add(fr::add(dd, dd), dd), prod[t - 3]);
+                        } else if (t >= 4 && consecutive && kdeg == 3) {
+                            Fr s = fr::add(prod[t - 1], prod[t - 3]);
+                            s = fr::add(s, s);
+                            s = fr::add(s, s);
+                            Fr m2 = fr::add(prod[t - 2], prod[t - 2]);
+                            Fr m6 = fr::add(fr::add(m2, m2), m2);
+                            prod[t] = fr::sub(fr::sub(s, m6), prod[t - 4]);
+                        } else {
+                            prod[t] = fr::mul(prod[t], cur);
+                            SC_NEXT_POINT(t)
+                        }
                     }
                 }
 #undef SC_NEXT_POINT

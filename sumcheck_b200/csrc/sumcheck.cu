@@ -275,56 +275,58 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
             TRY_P(cudaMemcpyAsync(p->tab0[j], tables[j], N * elem, cudaMemcpyHostToDevice, p->stream));
         }
     }
-    TRY_P(cudaMalloc(&p->slabA, (size_t)T * nA * elem));
-    TRY_P(cudaMalloc(&p->slabB, (size_t)T * nB * elem));
+    // Two allocations for everything else (creation cost matters for one-shot proofs and the two GKR phases):
+    // one device slab = ping-pong tables + all small arrays, one pinned+mapped host block.
+    const uint32_t nnz = offsets[n_products];
+    p->max_grid = g_dev[device].sms * 32;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += up(bytes ? bytes : 1); return o; };
+    const size_t oA = take((size_t)T * nA * elem), oB = take((size_t)T * nB * elem);
+    const size_t oP0 = take(T * sizeof(uint32_t*)), oPA = take(T * sizeof(uint32_t*)), oPB = take(T * sizeof(uint32_t*));
+    const size_t oOff = take((n_products + 1) * sizeof(uint32_t)), oIdx = take(nnz * sizeof(uint32_t)), oFirst = take(nnz);
+    const size_t oCoef = take((size_t)n_products * 32), oPart = take((size_t)p->max_grid * sck::MAX_NPTS * 32), oCnt = take(4);
+    const size_t oEv = take((size_t)(d + 1) * 32), oCa = take((size_t)(d + 1) * 32), oLag = take((size_t)2 * (d + 1) * 32);
+    const size_t oTe = take((size_t)nv * (d + 1) * 32), oTc = take((size_t)nv * 32), oSt = take(2 * sizeof(b2::State));
+    TRY_P(cudaMalloc(&p->slabA, off));
+    uint8_t* base = (uint8_t*)p->slabA;
     for (uint32_t j = 0; j < T; j++) {
-        p->bufA[j] = p->slabA + (size_t)j * nA * 8;
-        p->bufB[j] = p->slabB + (size_t)j * nB * 8;
+        p->bufA[j] = (uint32_t*)(base + oA) + (size_t)j * nA * 8;
+        p->bufB[j] = (uint32_t*)(base + oB) + (size_t)j * nB * 8;
     }
-    TRY_P(cudaMalloc(&p->d_ptr0, T * sizeof(uint32_t*)));
-    TRY_P(cudaMalloc(&p->d_ptrA, T * sizeof(uint32_t*)));
-    TRY_P(cudaMalloc(&p->d_ptrB, T * sizeof(uint32_t*)));
+    p->d_ptr0 = (uint32_t**)(base + oP0); p->d_ptrA = (uint32_t**)(base + oPA); p->d_ptrB = (uint32_t**)(base + oPB);
+    p->d_offsets = (uint32_t*)(base + oOff); p->d_indices = (uint32_t*)(base + oIdx); p->d_first = base + oFirst;
+    p->d_coeffs = (uint32_t*)(base + oCoef); p->d_partials = (uint32_t*)(base + oPart); p->d_counter = (unsigned int*)(base + oCnt);
+    p->d_evals = (uint32_t*)(base + oEv); p->d_canon = (uint32_t*)(base + oCa);
+    p->d_tail_evals = (uint32_t*)(base + oTe); p->d_tail_chal = (uint32_t*)(base + oTc); p->d_st = (b2::State*)(base + oSt);
     TRY_P(cudaMemcpyAsync(p->d_ptr0, p->tab0.data(), T * sizeof(uint32_t*), cudaMemcpyHostToDevice, p->stream));
     TRY_P(cudaMemcpyAsync(p->d_ptrA, p->bufA.data(), T * sizeof(uint32_t*), cudaMemcpyHostToDevice, p->stream));
     TRY_P(cudaMemcpyAsync(p->d_ptrB, p->bufB.data(), T * sizeof(uint32_t*), cudaMemcpyHostToDevice, p->stream));
-    const uint32_t nnz = offsets[n_products];
     std::vector<uint8_t> first(nnz, 0);
     {
         std::vector<uint8_t> seen(T, 0);
         for (uint32_t j = 0; j < nnz; j++)
             if (!seen[indices[j]]) { seen[indices[j]] = 1; first[j] = 1; }
     }
-    TRY_P(cudaMalloc(&p->d_offsets, (n_products + 1) * sizeof(uint32_t)));
-    TRY_P(cudaMalloc(&p->d_indices, nnz * sizeof(uint32_t)));
-    TRY_P(cudaMalloc(&p->d_first, nnz));
-    TRY_P(cudaMalloc(&p->d_coeffs, (size_t)n_products * 32));
     TRY_P(cudaMemcpyAsync(p->d_offsets, offsets, (n_products + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
     TRY_P(cudaMemcpyAsync(p->d_indices, indices, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, p->stream));
     TRY_P(cudaMemcpyAsync(p->d_first, first.data(), nnz, cudaMemcpyHostToDevice, p->stream));
     TRY_P(cudaMemcpyAsync(p->d_coeffs, coeffs, (size_t)n_products * 32, cudaMemcpyHostToDevice, p->stream));
-    p->max_grid = g_dev[device].sms * 32;
-    TRY_P(cudaMalloc(&p->d_partials, (size_t)p->max_grid * sck::MAX_NPTS * 32));
-    TRY_P(cudaMalloc(&p->d_counter, sizeof(unsigned int)));
     TRY_P(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned int), p->stream));
-    TRY_P(cudaMalloc(&p->d_evals, (size_t)(d + 1) * 32));
-    TRY_P(cudaMalloc(&p->d_canon, (size_t)(d + 1) * 32));
     if (d + 1 <= 32) {  // Lagrange weights for the P(1)-from-claim shortcut
-        TRY_P(cudaMalloc(&p->d_lagrange, (size_t)2 * (d + 1) * 32));
+        p->d_lagrange = (uint32_t*)(base + oLag);
         sck::lagrange_setup_kernel<<<1, 32, 0, p->stream>>>(d, p->d_lagrange);
         TRY_P(cudaGetLastError());
     }
-    TRY_P(cudaHostAlloc(&p->h_result, (size_t)(d + 1) * 64 + 64, cudaHostAllocMapped));
-    memset(p->h_result, 0, (size_t)(d + 1) * 64 + 64);
+    const size_t hRes = up((size_t)(d + 1) * 64 + 64), hTail = up((size_t)nv * (d + 2) * 32), hSt = up(2 * sizeof(b2::State));
+    TRY_P(cudaHostAlloc(&p->h_result, hRes + hTail + hSt, cudaHostAllocMapped));
+    memset(p->h_result, 0, hRes);
     TRY_P(cudaHostGetDevicePointer((void**)&p->d_result, p->h_result, 0));
     p->h_evals = p->h_result;
     p->h_canon = p->h_result + (size_t)(d + 1) * 8;
-    TRY_P(cudaMalloc(&p->d_tail_evals, (size_t)nv * (d + 1) * 32));
-    TRY_P(cudaMalloc(&p->d_tail_chal, (size_t)nv * 32));
-    TRY_P(cudaMallocHost(&p->h_tail, (size_t)nv * (d + 2) * 32));
-    TRY_P(cudaMalloc(&p->d_st, 2 * sizeof(b2::State)));
-    TRY_P(cudaMallocHost(&p->h_st, 2 * sizeof(b2::State)));
-    p->ev.resize(2 * (size_t)nv);
-    for (auto& e : p->ev) TRY_P(cudaEventCreate(&e));
+    p->h_tail = (uint32_t*)((uint8_t*)p->h_result + hRes);
+    p->h_st = (b2::State*)((uint8_t*)p->h_result + hRes + hTail);
+    p->ev.assign(2 * (size_t)nv, nullptr);  // CUDA events are created on demand (sc_prover_set_timing)
     p->round_ms.assign(nv, 0.f);
     p->randomness.reserve((size_t)nv * 4);
     TRY_P(cudaStreamSynchronize(p->stream));  // uploads done: the caller may free/modify its buffers
@@ -525,14 +527,8 @@ void sc_prover_destroy(sc_prover* p) {
     cudaFree(p->d_gather); cudaFree(p->d_evals_g); cudaFree(p->d_canon_g); cudaFree(p->d_fold); cudaFree(p->d_gather_tabs);
     cudaFree(p->d_sub_tabs);
     if (p->owns_tab0) cudaFree(p->slab0);
-    cudaFree(p->slabA); cudaFree(p->slabB);
-    cudaFree(p->d_ptr0); cudaFree(p->d_ptrA); cudaFree(p->d_ptrB);
-    cudaFree(p->d_offsets); cudaFree(p->d_indices); cudaFree(p->d_first); cudaFree(p->d_coeffs);
-    cudaFree(p->d_partials); cudaFree(p->d_counter); cudaFree(p->d_evals); cudaFree(p->d_canon); cudaFree(p->d_lagrange);
-    cudaFree(p->d_tail_evals); cudaFree(p->d_tail_chal); cudaFree(p->d_st);
-    if (p->h_tail) cudaFreeHost(p->h_tail);
-    if (p->h_st) cudaFreeHost(p->h_st);
-    if (p->h_result) cudaFreeHost(p->h_result);
+    cudaFree(p->slabA);  // one slab: ping-pong tables and every small device array
+    if (p->h_result) cudaFreeHost(p->h_result);  // one pinned block: results, tail read-back, transcript state
     for (auto e : p->ev) if (e) cudaEventDestroy(e);
     if (p->own_stream) cudaStreamDestroy(p->own_stream);
     delete p;
@@ -666,6 +662,11 @@ uint32_t sc_prover_round_times_ms(const sc_prover* p, float* out, uint32_t cap) 
 uint64_t sc_prover_launch_count(const sc_prover* p) { return p->launches; }
 int sc_prover_set_timing(sc_prover* p, int enabled) {
     p->want_timing = enabled != 0;
+    if (p->want_timing) {
+        CUDA_TRY(cudaSetDevice(p->device));
+        for (auto& e : p->ev)
+            if (!e) CUDA_TRY(cudaEventCreate(&e));
+    }
     return SC_OK;
 }
 
