@@ -32,6 +32,7 @@ extern "C" {
 #define SC_ERR_PANIC_MISSING_MSG (-3)     /* prover.rs:90-92  "verifier message is empty"           */
 #define SC_ERR_PANIC_NOT_ACTIVE (-4)      /* prover.rs:96-98  "Prover is not active"                */
 #define SC_ERR_BAD_INPUT (-5)             /* data_structures.rs:78,82 asserts; gkr mod.rs:28-29,100-101 asserts */
+#define SC_ERR_REJECT (-6)                /* verifier.rs:109-113 Error::Reject (sc_ml_verify only) */
 #define SC_ERR_CUDA (-10)                 /* CUDA runtime failure -> Error::OtherError (src/error.rs:19) */
 #define SC_ERR_NO_DEVICE (-11)            /* no usable sm_100 device: the library never falls back to the CPU */
 #define SC_ERR_COMM (-12)                 /* multi-GPU exchange failure */
@@ -146,6 +147,19 @@ int sc_gkr_start_phase2_sumcheck(sc_prover **out, uint32_t dim, const uint64_t *
 int sc_gkr_prove(sc_blake2b512_rng *rng, uint32_t dim, uint64_t nnz, const uint64_t *f1_idx, const uint64_t *f1_val,
                  const uint64_t *f2, const uint64_t *f3, const uint64_t *g, int device, uint64_t *phase1_out,
                  uint64_t *phase2_out, uint64_t *u_out, uint64_t *v_out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Verifier-side counterparts (what the reference's tests call right after proving). */
+/* ListOfProductsOfPolynomials::evaluate (src/ml_sumcheck/data_structures.rs:99-109): the polynomial at `point`
+ * (nv elements); every table is folded nv times on the device. */
+int sc_poly_evaluate(uint32_t nv, uint32_t n_tables, const uint64_t *const *tables, uint32_t n_products,
+                     const uint64_t *coeffs, const uint32_t *offsets, const uint32_t *indices, const uint64_t *point,
+                     int device, uint64_t out[4]);
+/* MLSumcheck::verify_as_subprotocol (src/ml_sumcheck/mod.rs:84-100) with check_and_generate_subclaim
+ * (verifier.rs:90-121).  evals: nv*(d+1)*4 u64 (the Proof).  Returns SC_ERR_REJECT when a round's P(0)+P(1) does not
+ * match; else SubClaim.point -> point_out (nv*4, nullable) and SubClaim.expected_evaluation -> expected_out. */
+int sc_ml_verify(sc_blake2b512_rng *rng, uint32_t nv, uint32_t d, const uint64_t claimed_sum[4], const uint64_t *evals,
+                 int device, uint64_t *point_out, uint64_t expected_out[4]);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Multi-GPU (one process per GPU).  The reference has no distributed path; this is the B200-native extension the

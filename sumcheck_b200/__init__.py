@@ -17,6 +17,7 @@ from .api import (  # noqa: F401
     ProverMsg,
     ProverState,
     SparseMultilinearExtension,
+    SubClaim,
     SumcheckError,
     VerifierMsg,
     initialize_phase_one,

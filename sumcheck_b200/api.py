@@ -138,6 +138,15 @@ class ListOfProductsOfPolynomials:
                 indexed.append(self._lookup[key])
         self.products.append((_elems(coefficient), indexed))
 
+    def evaluate(self, point, device=0):  # data_structures.rs:99-109, on the device
+        coeffs, offsets, indices = self._csr()
+        T = len(self.flattened_ml_extensions)
+        tabs = (C.c_void_p * max(T, 1))(*[t.ctypes.data for t in self.flattened_ml_extensions])
+        out = np.zeros(4, dtype=np.uint64)
+        _check(capi.lib().sc_poly_evaluate(self.num_variables, T, tabs, len(self.products), _p64(coeffs), _p32(offsets),
+                                           _p32(indices), _p64(_elems(point)), device, _p64(out)))
+        return out
+
     # what crosses the C ABI
     def _csr(self):
         coeffs = np.ascontiguousarray(np.stack([c for c, _ in self.products])) if self.products else np.zeros((0, 4), np.uint64)
@@ -158,6 +167,14 @@ class ProverMsg:
         n = self.evaluations.shape[0]
         b = _serialize_msgs(self.evaluations.reshape(1, n, 4))
         return b[8:]  # strip the outer Vec<ProverMsg> length
+
+
+class SubClaim:
+    """verifier.rs:29-34."""
+
+    def __init__(self, point, expected_evaluation):
+        self.point = point
+        self.expected_evaluation = expected_evaluation
 
 
 class VerifierMsg:
@@ -328,6 +345,22 @@ class MLSumcheck:
         # mod.rs:65-67 pushes the last challenge without folding
         _check(capi.lib().sc_prover_push_randomness(state._h, _p64(v_msg.randomness)))
         return msgs, state
+
+    @staticmethod
+    def verify(polynomial_info, claimed_sum, proof, device=0):  # mod.rs:73-80
+        return MLSumcheck.verify_as_subprotocol(Blake2b512Rng.setup(), polynomial_info, claimed_sum, proof, device)
+
+    @staticmethod
+    def verify_as_subprotocol(fs_rng, polynomial_info, claimed_sum, proof, device=0):  # mod.rs:84-100
+        nv, d = polynomial_info.num_variables, polynomial_info.max_multiplicands
+        if len(proof) < nv:
+            raise Panic(-4, "proof is incomplete")  # mod.rs:93
+        evals = np.ascontiguousarray(np.stack([m.evaluations for m in proof[:nv]]))
+        point = np.zeros((nv, 4), dtype=np.uint64)
+        expected = np.zeros(4, dtype=np.uint64)
+        _check(capi.lib().sc_ml_verify(C.byref(fs_rng.state), nv, d, _p64(_elems(claimed_sum)), _p64(evals), device, _p64(point),
+                                       _p64(expected)))
+        return SubClaim(point, expected)
 
     @staticmethod
     def serialize_proof(proof):

@@ -172,22 +172,53 @@ __global__ void sum_partials_kernel(const uint32_t* gathered, uint32_t n_ranks, 
         if (t == 0) *host_flag = seq;
     }
 }
-// out[j] = tab[j][0] + r * (tab[j][1] - tab[j][0])  for the T two-entry tables of a shard
-__global__ void fold_final_kernel(const uint32_t* const* tabs, uint32_t T, Fr8 r8, uint32_t* out) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= T) return;
+// ---- verifier-side helpers: ListOfProductsOfPolynomials::evaluate and check_and_generate_subclaim ----
+// DenseMultilinearExtension::fix_variables(&[r]) alone: out[b] = in[2b] + r (in[2b+1] - in[2b]); blockIdx.y = table
+__global__ void __launch_bounds__(128) fold_only_kernel(const uint32_t* const* tab_in, uint32_t* const* tab_out, unsigned long long n_out, Fr8 r8) {
+    __shared__ __align__(16) uint32_t s_foldC[64];
     Fr r;
 #pragma unroll
     for (int i = 0; i < 8; i++) r.l[i] = r8.l[i];
-    Fr a = fr::load(tabs[j]), b = fr::load(tabs[j] + 8);
-    fr::store(out + (size_t)j * 8, fr::add(a, fr::mul(r, fr::sub(b, a))));
+    prepare_fold_consts(r, s_foldC);
+    const uint32_t* in = tab_in[blockIdx.y];
+    uint32_t* out = tab_out[blockIdx.y];
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < n_out;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        Fr e0 = fr::load_stream(in + b * 16), e1 = fr::load_stream(in + b * 16 + 8);
+        fr::store(out + b * 8, fr::add(e0, fr::mul_round_const(s_foldC, fr::sub(e1, e0))));
+    }
 }
-// gathered[g][j] -> tables[j][g]
-__global__ void transpose_gather_kernel(const uint32_t* gathered, uint32_t n_ranks, uint32_t T, uint32_t* tables) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ranks * T) return;
-    uint32_t g = i / T, j = i % T;
-    fr::store(tables + ((size_t)j * n_ranks + g) * 8, fr::load(gathered + (size_t)i * 8));
+// sum_k c_k * prod_j value[idx] over the (fully folded, 1-element) tables  — data_structures.rs:100-108
+__global__ void poly_combine_kernel(const uint32_t* const* tabs, const uint32_t* offsets, const uint32_t* indices, const uint32_t* coeffs,
+                                    uint32_t n_products, uint32_t* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Fr sum = fr::zero();
+    for (uint32_t k = 0; k < n_products; k++) {
+        Fr pr = fr::load(coeffs + 8 * k);
+        for (uint32_t j = offsets[k]; j < offsets[k + 1]; j++) pr = fr::mul(pr, fr::load(tabs[indices[j]]));
+        sum = fr::add(sum, pr);
+    }
+    fr::store(out, sum);
+}
+// check_and_generate_subclaim (verifier.rs:90-121): for every round P(0)+P(1) == expected, expected = P(r_i) by
+// interpolation.  One warp.  result[0] = 0 accept / (1 + round) reject; expected_out = final expected evaluation.
+__global__ void verify_kernel(uint32_t nv, uint32_t d, const uint32_t* claimed, const uint32_t* evals, const uint32_t* rand,
+                              const uint32_t* lagrange, uint32_t* result, uint32_t* expected_out) {
+    __shared__ uint32_t scratch[32 * 8];
+    Fr expected = fr::load(claimed);
+    uint32_t bad = 0;
+    for (uint32_t i = 0; i < nv && !bad; i++) {
+        const uint32_t* ev = evals + (size_t)i * (d + 1) * 8;
+        Fr s = fr::add(fr::load(ev), fr::load(ev + 8));
+        if (!fr::eq(s, expected)) bad = 1 + i;   // identical on every lane
+        Fr nxt = claim_from_prev(ev, lagrange, fr::load(rand + (size_t)i * 8), d, scratch);
+#pragma unroll
+        for (int w = 0; w < 8; w++) expected.l[w] = __shfl_sync(0xffffffffu, nxt.l[w], 0);
+    }
+    if (threadIdx.x == 0) {
+        result[0] = bad;
+        fr::store(expected_out, expected);
+    }
 }
 
 // ---- merged sparse output for the stand-alone initialize_phase_one API: after sorting (key, position) by key,

@@ -106,9 +106,10 @@ struct sc_prover {
     // ---- multi-GPU (capi_multi.inc): nv is GLOBAL, nv_local = nv - log2(ranks) is what this rank's shard spans
     uint32_t nv_local = 0;
     struct sc_comm* comm = nullptr;
-    sc_prover* sub = nullptr;  // replicated prover for the last log2(ranks) rounds
-    uint32_t *d_gather = nullptr, *d_evals_g = nullptr, *d_canon_g = nullptr, *d_fold = nullptr, *d_gather_tabs = nullptr,
-             *d_sub_tabs = nullptr;
+    sc_prover* sub = nullptr;  // replicated prover for the last rounds
+    sc_prover* wait_on = nullptr;  // whose mapped result block the round just issued will signal (this or sub)
+    uint32_t switch_round = 0;     // first global round run replicated
+    uint32_t *d_gather = nullptr, *d_evals_g = nullptr, *d_canon_g = nullptr, *d_sub_tabs = nullptr;
     std::vector<uint64_t> h_coeffs;
     std::vector<uint32_t> h_offsets, h_indices;
 };
@@ -363,8 +364,9 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
     if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));
     if (p->direct_active) {
         // the last block wrote the message into mapped pinned memory and then the flag: spin instead of copy + sync
-        volatile uint32_t* flag = p->h_result + (size_t)(p->d + 1) * 16;
-        const uint32_t want = p->seq;
+        sc_prover* w = (p->comm && p->wait_on) ? p->wait_on : p;
+        volatile uint32_t* flag = w->h_result + (size_t)(p->d + 1) * 16;
+        const uint32_t want = w->seq;
         unsigned long long spins = 0;
         while (*flag != want) {
             if ((++spins & 0xfffff) == 0) {  // every ~1M polls make sure the kernel has not died
@@ -374,6 +376,7 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
             }
         }
         __sync_synchronize();
+        if (w != p) memcpy(p->h_result, w->h_result, (size_t)(p->d + 1) * 64);
         if (p->comm && comm_failed(p)) return fail(SC_ERR_COMM, "a peer GPU did not deliver its partial sums in time");
         return SC_OK;
     }
@@ -524,8 +527,7 @@ void sc_prover_destroy(sc_prover* p) {
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->sub) { p->sub->stream = p->sub->own_stream; sc_prover_destroy(p->sub); cudaSetDevice(p->device); }
-    cudaFree(p->d_gather); cudaFree(p->d_evals_g); cudaFree(p->d_canon_g); cudaFree(p->d_fold); cudaFree(p->d_gather_tabs);
-    cudaFree(p->d_sub_tabs);
+    cudaFree(p->d_gather); cudaFree(p->d_evals_g); cudaFree(p->d_canon_g); cudaFree(p->d_sub_tabs);
     if (p->owns_tab0) cudaFree(p->slab0);
     cudaFree(p->slabA);  // one slab: ping-pong tables and every small device array
     if (p->h_result) cudaFreeHost(p->h_result);  // one pinned block: results, tail read-back, transcript state
@@ -583,8 +585,10 @@ int sc_prover_push_randomness(sc_prover* p, const uint64_t r[4]) {
 int sc_prover_table(const sc_prover* p, uint32_t j, uint64_t* out, uint64_t cap_elems, uint64_t* len_out) {
     if (j >= p->T) return fail(SC_ERR_BAD_INPUT, "table %u out of range", j);
     // after round i >= 2 the tables have been folded i-1 times
-    if (p->comm && p->round > p->nv_local)
-        return fail(SC_ERR_BAD_INPUT, "sharded prover: tables are replicated on the sub-prover after round %u", p->nv_local);
+    if (p->comm && p->round >= p->switch_round) {  // replicated rounds: the full (small) tables live on the sub-prover
+        if (!p->sub) return fail(SC_ERR_BAD_INPUT, "sharded prover: no replicated state yet");
+        return sc_prover_table(p->sub, j, out, cap_elems, len_out);
+    }
     uint64_t len = p->round <= 1 ? p->N : (p->N >> (p->round - 1));  // sharded: this rank's shard
     if (len_out) *len_out = len;
     if (!out) return SC_OK;
@@ -674,3 +678,4 @@ int sc_prover_set_timing(sc_prover* p, int enabled) {
 
 #include "capi_gkr.inc"
 #include "capi_multi.inc"
+#include "capi_verify.inc"

@@ -182,6 +182,27 @@ def test_fused_tail_device_transcript(orc, monkeypatch, nv, n_products, m, pre):
     assert_same_proof(orc, build_poly(nv, opoly.tables, prods), opoly, pre_feed=pre)
 
 
+@pytest.mark.parametrize("nv,n_products,mult_range,shared", [(1, 3, (2, 5), False), (7, 4, (1, 6), True), (12, 5, (4, 9), False)])
+def test_prove_verify_evaluate_on_device(orc, nv, n_products, mult_range, shared):
+    """The reference's own acceptance test (test_polynomial, ml_sumcheck/test.rs:64-75) with every step on the device:
+    prove -> verify -> poly.evaluate(subclaim.point) == subclaim.expected_evaluation; each step also equals the oracle."""
+    tables, products = random_instance(900 + nv, nv, n_products, mult_range, shared)
+    poly, opoly = both_polys(orc, nv, tables, products)
+    proof = sc.MLSumcheck.prove(poly)
+    asserted = sc.MLSumcheck.extract_sum(proof)
+    sub = sc.MLSumcheck.verify(poly.info(), asserted, proof)
+    evals = np.stack([m.evaluations for m in proof])
+    opoint, oexp = orc.ml_verify(nv, poly.max_multiplicands, asserted, evals)
+    assert np.array_equal(sub.point, opoint) and np.array_equal(sub.expected_evaluation, oexp)
+    got = poly.evaluate(sub.point)
+    assert np.array_equal(got, sub.expected_evaluation)          # "wrong subclaim" check of the reference
+    assert np.array_equal(got, orc.poly_evaluate(opoly, opoint))
+    wrong = limbs((pm.from_mont_limbs(asserted) + 1) % pm.P)
+    with pytest.raises(sc.SumcheckError) as e:                    # Error::Reject (verifier.rs:109-113)
+        sc.MLSumcheck.verify(poly.info(), wrong, proof)
+    assert e.value.code == -6
+
+
 def test_reset_reproves_identically(orc):
     nv = 10
     tabs = [orc.synth_table(1 << nv, 900 + j) for j in range(3)]
