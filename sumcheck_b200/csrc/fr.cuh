@@ -251,7 +251,7 @@ __device__ __forceinline__ void wide_zero(WideAcc& w) {
 }
 
 // w += a * b   (integer product, 16 limbs): 64 IMAD.WIDE + 33 carry-chained adds
-#ifdef FR_COMPACT
+#if defined(FR_COMPACT) && !defined(FR_INLINE_WIDE_MAC)
 static __device__ __noinline__ WideAcc wide_mac_outlined(WideAcc w, Fr a, Fr b) {
     wide_mac_limbs(w.l, a.l, b.l);
     return w;

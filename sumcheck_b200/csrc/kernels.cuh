@@ -57,6 +57,9 @@ struct RoundParams {
     uint32_t* comm_error;           // mapped host word set to 1 when a peer does not answer in time
     const uint32_t* prev_evals;     // [(d+1)][8] previous round's ProverMsg (may alias evals_out: read first)
     const uint32_t* lagrange;       // [2][(d+1)][8]: w_j = 1/prod_{k!=j}(j-k), then the field elements 0..d
+    // TMA + tensor-core fold rounds (tc_round.cuh): [n_tables] CUtensorMap descriptors of tab_in (128-byte rows,
+    // SWIZZLE_128B, 128-row boxes); null for the plain kernels
+    const void* tmaps;
 };
 
 // P_prev(r) by Lagrange interpolation through (j, prev[j]), j = 0..d — what the verifier computes at
@@ -156,6 +159,72 @@ __device__ __forceinline__ void prepare_fold_consts(const Fr& r, uint32_t* foldC
     __syncthreads();
 }
 
+// One multiplicand's pair (v0, v1) = (table[2b], table[2b+1]) of product k enters the running product terms of all
+// evaluation points (prover.rs:116-128).  first/last: position of the multiplicand inside its product; kdeg: how many
+// multiplicands the running product holds once this one is in.
+template <int NPTS>
+__device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, bool first, bool last, uint32_t kdeg, const Fr& v0,
+                                             const Fr& v1, Fr (&prod)[NPTS], fr::WideAcc (&accw)[NPTS]) {
+    // prover.rs:119-124: start = table[2b], step = table[2b+1] - start; product[t] *= start; start += step
+    Fr step = fr::sub(v1, v0);
+    Fr cur = v0;
+    for (uint32_t s = 0; s < p.t0; s++) cur = fr::add(cur, step);  // only for d+1 > MAX_NPTS
+    if (first && !p.defer_coeff) {  // c_k * prod_j(...): scale the first multiplicand's line once
+        Fr c = fr::load(p.coeffs + 8 * k);
+        cur = fr::mul(cur, c);
+        step = fr::mul(step, c);
+    }
+    // slot s holds evaluation point t0+s, or with skip1 the points 0, 2, 3, ..: one extra step after slot 0
+#define SC_NEXT_POINT(t)                                        \
+    if ((t) + 1 < NPTS) {                                       \
+        cur = fr::add(cur, step);                               \
+        if ((t) == 0 && p.skip1) cur = fr::add(cur, step);      \
+    }
+    if (first && last) {  // single multiplicand: contributes its value itself
+#pragma unroll
+        for (int t = 0; t < NPTS; t++) {
+            fr::wide_add_shifted(accw[t], cur);
+            SC_NEXT_POINT(t)
+        }
+    } else if (first) {
+#pragma unroll
+        for (int t = 0; t < NPTS; t++) {
+            prod[t] = cur;
+            SC_NEXT_POINT(t)
+        }
+    } else if (last) {  // prover.rs:126-128 fused with the last multiply: products_sum[t] += product[t]*start
+#pragma unroll
+        for (int t = 0; t < NPTS; t++) {
+            fr::wide_mac(accw[t], prod[t], cur);
+            SC_NEXT_POINT(t)
+        }
+    } else {
+        // After k multiplicands prod[.] is a degree-k polynomial in the evaluation point, so on consecutive
+        // points only k+1 values need a multiply; the others follow by finite differences (integer
+        // combinations, exact): k = 2: q(t) = 3(q(t-1) - q(t-2)) + q(t-3);  k = 3: q(t) = 4(q(t-1) + q(t-3)) -
+        // 6 q(t-2) - q(t-4).  Saves one of the four multiplies of round 1 at degree 3.
+        const bool consecutive = !p.skip1;
+#pragma unroll
+        for (int t = 0; t < NPTS; t++) {
+            if (t >= 3 && consecutive && kdeg == 2) {
+                Fr dd = fr::sub(prod[t - 1], prod[t - 2]);
+                prod[t] = fr::add(fr::add(fr::add(dd, dd), dd), prod[t - 3]);
+            } else if (t >= 4 && consecutive && kdeg == 3) {
+                Fr s = fr::add(prod[t - 1], prod[t - 3]);
+                s = fr::add(s, s);
+                s = fr::add(s, s);
+                Fr m2 = fr::add(prod[t - 2], prod[t - 2]);
+                Fr m6 = fr::add(fr::add(m2, m2), m2);
+                prod[t] = fr::sub(fr::sub(s, m6), prod[t - 4]);
+            } else {
+                prod[t] = fr::mul(prod[t], cur);
+                SC_NEXT_POINT(t)
+            }
+        }
+    }
+#undef SC_NEXT_POINT
+}
+
 template <int NPTS, bool FOLD, bool STREAM>
 __device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const uint32_t* foldC, unsigned long long b0,
                                                  unsigned long long stride, fr::WideAcc (&accw)[NPTS]) {
@@ -187,66 +256,7 @@ __device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const uin
                     v0 = fr::load_stream(src);
                     v1 = fr::load_stream(src + 8);
                 }
-                // prover.rs:119-124: start = table[2b], step = table[2b+1] - start; product[t] *= start; start += step
-                Fr step = fr::sub(v1, v0);
-                Fr cur = v0;
-                for (uint32_t s = 0; s < p.t0; s++) cur = fr::add(cur, step);  // only for d+1 > MAX_NPTS
-                const bool first = (jj == j0), last = (jj + 1 == j1);
-                if (first && !p.defer_coeff) {  // c_k * prod_j(...): scale the first multiplicand's line once
-                    Fr c = fr::load(p.coeffs + 8 * k);
-                    cur = fr::mul(cur, c);
-                    step = fr::mul(step, c);
-                }
-                // slot s holds evaluation point t0+s, or with skip1 the points 0, 2, 3, ..: one extra step after slot 0
-#define SC_NEXT_POINT(t)                                        \
-    if ((t) + 1 < NPTS) {                                       \
-        cur = fr::add(cur, step);                               \
-        if ((t) == 0 && p.skip1) cur = fr::add(cur, step);      \
-    }
-                if (first && last) {  // single multiplicand: contributes its value itself
-#pragma unroll
-                    for (int t = 0; t < NPTS; t++) {
-                        fr::wide_add_shifted(accw[t], cur);
-                        SC_NEXT_POINT(t)
-                    }
-                } else if (first) {
-#pragma unroll
-                    for (int t = 0; t < NPTS; t++) {
-                        prod[t] = cur;
-                        SC_NEXT_POINT(t)
-                    }
-                } else if (last) {  // prover.rs:126-128 fused with the last multiply: products_sum[t] += product[t]*start
-#pragma unroll
-                    for (int t = 0; t < NPTS; t++) {
-                        fr::wide_mac(accw[t], prod[t], cur);
-                        SC_NEXT_POINT(t)
-                    }
-                } else {
-                    // After k multiplicands prod[.] is a degree-k polynomial in the evaluation point, so on consecutive
-                    // points only k+1 values need a multiply; the others follow by finite differences (integer
-                    // combinations, exact): k = 2: q(t) = 3(q(t-1) - q(t-2)) + q(t-3);  k = 3: q(t) = 4(q(t-1) + q(t-3)) -
-                    // 6 q(t-2) - q(t-4).  Saves one of the four multiplies of round 1 at degree 3.
-                    const uint32_t kdeg = jj - j0 + 1;
-                    const bool consecutive = !p.skip1;
-#pragma unroll
-                    for (int t = 0; t < NPTS; t++) {
-                        if (t >= 3 && consecutive && kdeg == 2) {
-                            Fr dd = fr::sub(prod[t - 1], prod[t - 2]);
-                            prod[t] = fr::add(fr::add(fr::add(dd, dd), dd), prod[t - 3]);
-                        } else if (t >= 4 && consecutive && kdeg == 3) {
-                            Fr s = fr::add(prod[t - 1], prod[t - 3]);
-                            s = fr::add(s, s);
-                            s = fr::add(s, s);
-                            Fr m2 = fr::add(prod[t - 2], prod[t - 2]);
-                            Fr m6 = fr::add(fr::add(m2, m2), m2);
-                            prod[t] = fr::sub(fr::sub(s, m6), prod[t - 4]);
-                        } else {
-                            prod[t] = fr::mul(prod[t], cur);
-                            SC_NEXT_POINT(t)
-                        }
-                    }
-                }
-#undef SC_NEXT_POINT
+                consume_pair<NPTS>(p, k, jj == j0, jj + 1 == j1, jj - j0 + 1, v0, v1, prod, accw);
             }
         }
     }
@@ -368,24 +378,11 @@ __device__ __forceinline__ void exchange_partials(const RoundParams& p, Fr (&acc
     __syncwarp();
 }
 
-template <int NPTS, bool FOLD>
-__global__ void __launch_bounds__(SC_THREADS, SC_MIN_BLOCKS) round_kernel(const RoundParams p) {
-    __shared__ uint32_t s_red[32 * NPTS * 8];
-    __shared__ bool s_last;
-
-    // Per-thread sums are kept UNREDUCED (fr::WideAcc): the last multiply of every product term is a plain 256x256-bit
-    // integer product added into 17 limbs; one Montgomery reduction per evaluation point per thread at the end.
-    fr::WideAcc accw[NPTS];
-#pragma unroll
-    for (int t = 0; t < NPTS; t++) fr::wide_zero(accw[t]);
-    __shared__ __align__(16) uint32_t s_foldC[64];
-    Fr r;
-#pragma unroll
-    for (int i = 0; i < 8; i++) r.l[i] = p.r[i];
-    if (FOLD) prepare_fold_consts(r, s_foldC);
-
-    accumulate_pairs<NPTS, FOLD, true>(p, s_foldC, (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x,
-                                       (unsigned long long)gridDim.x * blockDim.x, accw);
+// Everything after the hot loop: per-thread lazy sums -> field elements -> block sum -> (last block) grid sum ->
+// (sharded) exchange with the peer GPUs -> deferred coefficient, P(1) from the claim, publication.
+template <int NPTS>
+__device__ __forceinline__ void finish_round(const RoundParams& p, fr::WideAcc (&accw)[NPTS], const Fr& r, uint32_t* s_red, bool* s_last_p) {
+    bool& s_last = *s_last_p;
     Fr acc[NPTS];
 #pragma unroll
     for (int t = 0; t < NPTS; t++) acc[t] = fr::wide_reduce(accw[t]);
@@ -417,6 +414,27 @@ __global__ void __launch_bounds__(SC_THREADS, SC_MIN_BLOCKS) round_kernel(const 
     // deferred coefficient, P(1) from the claim, both output forms; with a flag the message also goes to mapped host memory
     publish_round<NPTS>(p, acc, r, s_red, nullptr);
     if (threadIdx.x == 0 && p.host_flag) *p.host_flag = p.seq;
+}
+
+template <int NPTS, bool FOLD>
+__global__ void __launch_bounds__(SC_THREADS, SC_MIN_BLOCKS) round_kernel(const RoundParams p) {
+    __shared__ uint32_t s_red[32 * NPTS * 8];
+    __shared__ bool s_last;
+
+    // Per-thread sums are kept UNREDUCED (fr::WideAcc): the last multiply of every product term is a plain 256x256-bit
+    // integer product added into 17 limbs; one Montgomery reduction per evaluation point per thread at the end.
+    fr::WideAcc accw[NPTS];
+#pragma unroll
+    for (int t = 0; t < NPTS; t++) fr::wide_zero(accw[t]);
+    __shared__ __align__(16) uint32_t s_foldC[64];
+    Fr r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.l[i] = p.r[i];
+    if (FOLD) prepare_fold_consts(r, s_foldC);
+
+    accumulate_pairs<NPTS, FOLD, true>(p, s_foldC, (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x,
+                                       (unsigned long long)gridDim.x * blockDim.x, accw);
+    finish_round<NPTS>(p, accw, r, s_red, &s_last);
 }
 
 // Lagrange data for claim_from_prev: w_j = 1 / prod_{k != j} (j - k) and the field elements 0..d (one thread per j).

@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "gkr_kernels.cuh"
 #include "tail_params.cuh"
+#include "tmap_host.h"
 
 static_assert(sizeof(sc_blake2b512_rng) == sizeof(b2::State), "sc_blake2b512_rng must be layout-identical to b2::State");
 
@@ -90,6 +91,11 @@ struct sc_prover {
     uint32_t *d_tail_evals = nullptr, *d_tail_chal = nullptr, *h_tail = nullptr;
     b2::State *d_st = nullptr, *h_st = nullptr;
     int max_grid = 0;
+    // TMA descriptors of every table in each of the three buffers (tab0, A, B): [3][T] CUtensorMap in device memory;
+    // tc_buf_ok[c]: rounds reading buffer c may use the TMA + tensor-core fold kernel (tc_round.cuh)
+    uint8_t* d_maps = nullptr;
+    bool tc_buf_ok[3] = {false, false, false};
+    unsigned long long tc_min_pairs = 0;
     int cur = 0;  // which buffer holds the current tables: 0 = tab0, 1 = A, 2 = B
     cudaStream_t stream = nullptr;      // the stream work is issued on
     cudaStream_t own_stream = nullptr;  // created by the handle
@@ -189,6 +195,12 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
         rp.write_fold = 1;
         if (direct) rp.host_flag = p->d_result + (size_t)(p->d + 1) * 16;
         cudaError_t e;
+        if (p->tc_buf_ok[p->cur] && rp.n_pairs >= p->tc_min_pairs) {
+            // large fold round: tables staged by TMA, fix_variables on the tensor cores (tc_round.cuh)
+            rp.tmaps = p->d_maps + (size_t)p->cur * p->T * sizeof(CUtensorMap);
+            p->launches++;
+            e = sck::launch_fold_round_tc(p->d, g_dev[p->device].sms, p->max_grid, rp, p->stream);
+        } else
         switch (p->d) {
             case 1: e = launch_round<1>(p, true, rp); break;
             case 2: e = launch_round<2>(p, true, rp); break;
@@ -289,6 +301,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     const size_t oCoef = take((size_t)n_products * 32), oPart = take((size_t)p->max_grid * sck::MAX_NPTS * 32), oCnt = take(4);
     const size_t oEv = take((size_t)(d + 1) * 32), oCa = take((size_t)(d + 1) * 32), oLag = take((size_t)2 * (d + 1) * 32);
     const size_t oTe = take((size_t)nv * (d + 1) * 32), oTc = take((size_t)nv * 32), oSt = take(2 * sizeof(b2::State));
+    const size_t oMaps = take((size_t)3 * T * sizeof(CUtensorMap));
     TRY_P(cudaMalloc(&p->slabA, off));
     uint8_t* base = (uint8_t*)p->slabA;
     for (uint32_t j = 0; j < T; j++) {
@@ -300,6 +313,27 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     p->d_coeffs = (uint32_t*)(base + oCoef); p->d_partials = (uint32_t*)(base + oPart); p->d_counter = (unsigned int*)(base + oCnt);
     p->d_evals = (uint32_t*)(base + oEv); p->d_canon = (uint32_t*)(base + oCa);
     p->d_tail_evals = (uint32_t*)(base + oTe); p->d_tail_chal = (uint32_t*)(base + oTc); p->d_st = (b2::State*)(base + oSt);
+    {
+        // TMA descriptors (fold rounds with >= tc_min_pairs output pairs run on the TMA + tensor-core kernel)
+        static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+        p->d_maps = base + oMaps;
+        const char* env = getenv("SC_TC_MIN_PAIRS");
+        p->tc_min_pairs = env ? strtoull(env, nullptr, 10) : sck::tc_min_pairs();
+        if (p->tc_min_pairs < 128) p->tc_min_pairs = 128;
+        std::vector<CUtensorMap> maps((size_t)3 * T);
+        const size_t len[3] = {N, nA, nB};
+        for (int c = 0; c < 3 && !getenv("SC_NO_TC"); c++) {
+            const uint64_t rows = len[c] / 4;
+            bool ok = rows >= 128;
+            for (uint32_t j = 0; j < T && ok; j++) {
+                const uint32_t* tb = c == 0 ? p->tab0[j] : (c == 1 ? p->bufA[j] : p->bufB[j]);
+                ok = tmaph::make_table_map(&maps[(size_t)c * T + j], tb, rows, 128);
+            }
+            p->tc_buf_ok[c] = ok;
+        }
+        TRY_P(cudaMemcpyAsync(p->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, p->stream));
+        TRY_P(cudaStreamSynchronize(p->stream));  // `maps` is pageable and goes out of scope
+    }
     TRY_P(cudaMemcpyAsync(p->d_ptr0, p->tab0.data(), T * sizeof(uint32_t*), cudaMemcpyHostToDevice, p->stream));
     TRY_P(cudaMemcpyAsync(p->d_ptrA, p->bufA.data(), T * sizeof(uint32_t*), cudaMemcpyHostToDevice, p->stream));
     TRY_P(cudaMemcpyAsync(p->d_ptrB, p->bufB.data(), T * sizeof(uint32_t*), cudaMemcpyHostToDevice, p->stream));

@@ -1,10 +1,14 @@
 // Translation unit of the fused tail kernel (see tail_kernel.cuh).  Built with -DFR_COMPACT.
-#ifndef FR_COMPACT
+#if !defined(FR_COMPACT) && !defined(FR_COMPACT_OFF)
 #error "tail.cu must be compiled with -DFR_COMPACT"
 #endif
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "tail_kernel.cuh"
+#include "tc_round.cuh"
 
 namespace sck {
 
@@ -35,6 +39,76 @@ cudaError_t launch_fold_round(uint32_t npts, int grid, const RoundParams& rp, cu
         case 4: round_kernel<4, true><<<grid, ROUND_THREADS, 0, stream>>>(rp); break;
         case 5: round_kernel<5, true><<<grid, ROUND_THREADS, 0, stream>>>(rp); break;
         default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// TMA + tensor-core fold rounds (tc_round.cuh): 128 threads, TC_DYN_SMEM bytes of dynamic shared memory
+unsigned long long tc_min_pairs() { return TC_MIN_PAIRS; }
+
+template <int NPTS>
+static cudaError_t tc_prepare(int* occ) {
+    static bool ready_dev[64] = {};
+    static int blocks_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    bool& ready = ready_dev[dev];  // function attributes are per device
+    int& blocks = blocks_dev[dev];
+    if (!ready) {
+        cudaError_t e = cudaFuncSetAttribute(round_tc_kernel<NPTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_DYN_SMEM);
+        if (e != cudaSuccess) return e;
+        // three CTAs of ~58 KB each per SM: ask for the largest shared-memory carve-out (the default heuristic sizes it
+        // for one CTA and would leave the SM with a single resident block)
+        e = cudaFuncSetAttribute(round_tc_kernel<NPTS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        // Resident CTAs per SM, by hand: cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel on
+        // B200 whatever the shared-memory size (measured; three CTAs do co-reside and run 2x faster than one), so the
+        // limits are taken from the function and device attributes: registers, shared memory, tensor-memory columns.
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, round_tc_kernel<NPTS>);
+        if (e != cudaSuccess) return e;
+        int regs_sm = 0, smem_sm = 0;
+        cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * (int)TC_THREADS;
+        const int smem_cta = (int)fa.sharedSizeBytes + (int)TC_DYN_SMEM + 1024;  // + the per-CTA system reservation
+        blocks = regs_sm / regs_cta;
+        if (smem_sm / smem_cta < blocks) blocks = smem_sm / smem_cta;
+        if ((int)(512 / TC_TMEM_COLS) < blocks) blocks = 512 / TC_TMEM_COLS;
+        if (blocks < 1) blocks = 1;
+        if (getenv("SC_DEBUG"))
+            fprintf(stderr, "round_tc_kernel<%d>: %d CTAs/SM (regs %d, static smem %zu, dynamic smem %zu)\n", NPTS, blocks, fa.numRegs,
+                    fa.sharedSizeBytes, (size_t)TC_DYN_SMEM);
+        if (const char* f = getenv("SC_TC_OCC")) blocks = atoi(f);
+        ready = true;
+    }
+    *occ = blocks;
+    return cudaSuccess;
+}
+
+cudaError_t launch_fold_round_tc(uint32_t npts, int sms, int max_grid, const RoundParams& rp, cudaStream_t stream) {
+    int occ = 1;
+    cudaError_t e;
+    switch (npts) {
+        case 1: e = tc_prepare<1>(&occ); break;
+        case 2: e = tc_prepare<2>(&occ); break;
+        case 3: e = tc_prepare<3>(&occ); break;
+        case 4: e = tc_prepare<4>(&occ); break;
+        case 5: e = tc_prepare<5>(&occ); break;
+        default: return cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
+    const unsigned long long n_tiles = rp.n_pairs / tcf::TILE_ROWS;
+    unsigned long long cap = (unsigned long long)sms * occ;
+    if (cap > (unsigned long long)max_grid) cap = max_grid;
+    const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+    switch (npts) {
+        case 1: round_tc_kernel<1><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp); break;
+        case 2: round_tc_kernel<2><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp); break;
+        case 3: round_tc_kernel<3><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp); break;
+        case 4: round_tc_kernel<4><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp); break;
+        default: round_tc_kernel<5><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp); break;
     }
     return cudaGetLastError();
 }

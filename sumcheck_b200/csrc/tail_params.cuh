@@ -25,6 +25,8 @@ cudaError_t tail_init_constants();
 int fold_round_occupancy(uint32_t npts);
 int fold_round_threads();
 cudaError_t launch_fold_round(uint32_t npts, int grid, const RoundParams& rp, cudaStream_t stream);
+unsigned long long tc_min_pairs();
+cudaError_t launch_fold_round_tc(uint32_t npts, int sms, int max_grid, const RoundParams& rp, cudaStream_t stream);
 cudaError_t launch_tail(uint32_t degree, const TailParams& tp, cudaStream_t stream);
 
 }  // namespace sck
