@@ -123,6 +123,10 @@ int sc_prover_set_timing(sc_prover *p, int enabled);
 uint32_t sc_prover_round_times_ms(const sc_prover *p, float *out, uint32_t cap);
 /* Number of kernels launched by this handle since creation/reset. */
 uint64_t sc_prover_launch_count(const sc_prover *p);
+/* How many of those were fold rounds run by the TMA + tensor-core kernel (tcgen05.mma fix_variables; rounds with at
+ * least SC_TC_MIN_PAIRS output pairs, default 2^14).  Environment: SC_NO_TC=1 keeps every round on the plain kernels,
+ * SC_TC_MIN_PAIRS=<n> moves the threshold (tests use 128 to cover the path at small sizes). */
+uint64_t sc_prover_tc_round_count(const sc_prover *p);
 
 /* ------------------------------------------------------------------------------------------------------------
  * GKRRoundSumcheck (src/gkr_round_sumcheck/mod.rs).  f1: SparseMultilinearExtension over 3*dim variables as nnz

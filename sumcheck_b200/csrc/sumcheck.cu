@@ -106,7 +106,7 @@ struct sc_prover {
     bool direct_results = true;  // rounds deliver their message through mapped host memory + flag
     bool direct_active = false;  // ... and the round just issued did so
     bool exchange = false;       // sharded round: fuse the partial-sum exchange into the round kernel
-    uint64_t launches = 0;
+    uint64_t launches = 0, tc_rounds = 0;
     // where the d+1 results of the last round live on the device (local buffers, the summed copies, or the sub-prover's)
     uint32_t *out_evals = nullptr, *out_canon = nullptr;
     // ---- multi-GPU (capi_multi.inc): nv is GLOBAL, nv_local = nv - log2(ranks) is what this rank's shard spans
@@ -199,6 +199,7 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
             // large fold round: tables staged by TMA, fix_variables on the tensor cores (tc_round.cuh)
             rp.tmaps = p->d_maps + (size_t)p->cur * p->T * sizeof(CUtensorMap);
             p->launches++;
+            p->tc_rounds++;
             e = sck::launch_fold_round_tc(p->d, g_dev[p->device].sms, p->max_grid, rp, p->stream);
         } else
         switch (p->d) {
@@ -575,6 +576,7 @@ int sc_prover_reset(sc_prover* p) {
     p->cur = 0;
     p->randomness.clear();
     p->launches = 0;
+    p->tc_rounds = 0;
     return SC_OK;
 }
 
@@ -698,6 +700,7 @@ uint32_t sc_prover_round_times_ms(const sc_prover* p, float* out, uint32_t cap) 
     return p->nv;
 }
 uint64_t sc_prover_launch_count(const sc_prover* p) { return p->launches; }
+uint64_t sc_prover_tc_round_count(const sc_prover* p) { return p->tc_rounds; }
 int sc_prover_set_timing(sc_prover* p, int enabled) {
     p->want_timing = enabled != 0;
     if (p->want_timing) {

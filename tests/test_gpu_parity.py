@@ -203,6 +203,65 @@ def test_prove_verify_evaluate_on_device(orc, nv, n_products, mult_range, shared
     assert e.value.code == -6
 
 
+# ------------------------------------------------------------------------------------------- tensor-core fold rounds
+@pytest.mark.parametrize("nv,n_products,mult_range,shared", [
+    (9, 1, (3, 4), False),     # smallest shape with a 128-pair fold round (round 2 of nv=9): one tile, one CTA
+    (10, 1, (1, 2), False),    # single multiplicand
+    (11, 1, (2, 3), False),
+    (12, 1, (5, 6), False),    # d = 5: five summed points per launch
+    (12, 5, (1, 6), True),     # shared tables, repeats inside a product, short products: tiles staged once per use
+    (13, 3, (2, 5), False),    # several products, different lengths
+    (12, 2, (6, 8), False),    # d+1 > 6: no claim shortcut, rounds stay on the plain kernels (must still agree)
+])
+def test_tensor_core_fold_rounds(orc, monkeypatch, nv, n_products, mult_range, shared):
+    """Fold rounds on the TMA + tcgen05.mma kernel (csrc/tc_round.cuh), forced down to 128-pair rounds with
+    SC_TC_MIN_PAIRS so that small shapes cover one tile per CTA, several tiles per CTA and grid > tiles.  Same bytes as
+    the oracle, the same folded tables, and identical to the plain kernels (SC_NO_TC=1)."""
+    monkeypatch.setenv("SC_TC_MIN_PAIRS", "128")
+    tables, products = random_instance(7000 + 13 * nv + n_products, nv, n_products, mult_range, shared)
+    poly, opoly = both_polys(orc, nv, tables, products)
+    got, rand = assert_same_proof(orc, poly, opoly)
+    st = sc.IPForMLSumcheck.prover_init(poly)
+    import ctypes as C
+    ev = np.zeros((nv, poly.max_multiplicands + 1, 4), dtype=np.uint64)
+    rng = sc.Blake2b512Rng.setup()
+    assert sc.lib().sc_ml_prove(st._h, C.byref(rng.state), ev.ctypes.data_as(sc.capi.U64P), None) == 0
+    assert np.array_equal(ev, got)
+    want_tc = max(0, nv - 8) if poly.max_multiplicands <= 5 else 0   # rounds 2 .. nv-7 have >= 128 output pairs
+    assert st.tc_round_count() == want_tc
+    monkeypatch.setenv("SC_NO_TC", "1")
+    st2 = sc.IPForMLSumcheck.prover_init(poly)
+    rng = sc.Blake2b512Rng.setup()
+    ev2 = np.zeros_like(ev)
+    assert sc.lib().sc_ml_prove(st2._h, C.byref(rng.state), ev2.ctypes.data_as(sc.capi.U64P), None) == 0
+    assert st2.tc_round_count() == 0
+    assert np.array_equal(ev2, ev)
+
+
+def test_tensor_core_fold_special_values_and_edge_challenges(orc, monkeypatch):
+    """0 / 1 / p-1 tables (all-0x00 and near-all-0xff bytes in the u8 operand) and challenges 0, 1, p-1 (constants
+    matrix of zeros / of 2^(8k) mod p) through the interactive API; folded tables compared after every round."""
+    monkeypatch.setenv("SC_TC_MIN_PAIRS", "128")
+    nv = 10
+    rnd = random.Random(11)
+    pool = [0, 1, pm.P - 1, 2, pm.P - 2, (1 << 248) - 1, pm.P >> 1]
+    tables = [[rnd.choice(pool) for _ in range(1 << nv)] for _ in range(3)]
+    products = [(pm.P - 1, [0, 1, 2]), (1, [2, 2]), (0, [1])]
+    poly, opoly = both_polys(orc, nv, tables, products)
+    st, ost = sc.IPForMLSumcheck.prover_init(poly), orc.Prover(opoly)
+    chal = [0, 1, pm.P - 1, rnd.randrange(pm.P)]
+    v_msg = None
+    for i in range(5):
+        m = sc.IPForMLSumcheck.prove_round(st, v_msg)
+        om = ost.prove_round(None if v_msg is None else v_msg.randomness)
+        assert np.array_equal(m.evaluations, om)
+        for j, ft in enumerate(poly.flattened_ml_extensions):
+            k = next(k for k, t in enumerate(opoly.tables) if t is ft)
+            assert np.array_equal(st.table(j), ost.table(k))
+        v_msg = sc.VerifierMsg(limbs(chal[i % len(chal)]))
+    assert st.tc_round_count() == 2   # rounds 2 and 3 of nv=10 (256 and 128 output pairs)
+
+
 def test_reset_reproves_identically(orc):
     nv = 10
     tabs = [orc.synth_table(1 << nv, 900 + j) for j in range(3)]
@@ -266,6 +325,10 @@ def test_full_size_configs(orc, cfg, nv, n_products, m):
     finally:
         orc.set_threads(1)
     assert np.array_equal(got, evals)
+    st = sc.IPForMLSumcheck.prover_init(poly)
+    for i in range(3):
+        sc.IPForMLSumcheck.prove_round(st, None if i == 0 else sc.VerifierMsg(limbs(3 + i)))
+    assert st.tc_round_count() == 2   # the large fold rounds run on the TMA + tensor-core kernel
 
 
 # ------------------------------------------------------------------------------------------- GKR
