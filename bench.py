@@ -191,10 +191,13 @@ def main():
         peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    # dominant kernel: sck::round_kernel<3,true> (fused fold+sum; 3 summed points, P(1) from the claim), launched in rounds
-    # 2..nv; aggregate over its launches
-    fold_bytes = sum(algorithmic_bytes(nv, T, i) for i in range(2, nv + 1))
-    fold_ms = float(round_ms[1:].sum())
+    # dominant kernel: sck::round_tc_kernel<3> (TMA-staged tables, fix_variables on the tensor cores, fused with the
+    # 3-point sum; P(1) from the claim), launched in rounds 2..1+n_tc (the rounds with >= 2^14 output pairs); aggregate
+    # over its launches.  The remaining small rounds run sck::round_kernel<3,true> and are latency-bound.
+    n_tc = st.tc_round_count()  # of the last proof (reset() clears the counters)
+    tc_rounds = list(range(2, 2 + n_tc)) if n_tc else list(range(2, nv + 1))
+    fold_bytes = sum(algorithmic_bytes(nv, T, i) for i in tc_rounds)
+    fold_ms = float(sum(round_ms[i - 1] for i in tc_rounds))
     ach = fold_bytes / (fold_ms * 1e-3) / 1e9
     r2 = algorithmic_bytes(nv, T, 2) / (round_ms[1] * 1e-3) / 1e9
     r1 = algorithmic_bytes(nv, T, 1) / (round_ms[0] * 1e-3) / 1e9
@@ -211,12 +214,14 @@ def main():
                    "upload_ms_excluded": upload_ms, "proofs_per_s": 1e3 / ms_step, "hypercube_points_per_s": N / (ms_step * 1e-3),
                    "kernel_ms_per_step": float(round_ms.sum()), "round_ms": [round(float(x), 4) for x in round_ms]},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                     "kernel": "sck::round_kernel<3,true> (fused fold+sum), rounds 2..nv aggregated",
+                     "kernel": (f"sck::round_tc_kernel<3> (TMA + tcgen05.mma fold fused with the sum), rounds 2..{1 + n_tc} aggregated"
+                                if n_tc else "sck::round_kernel<3,true> (fused fold+sum), rounds 2..nv aggregated"),
+                     "small_rounds_ms": float(round_ms[1 + n_tc:].sum()) if n_tc else 0.0,
                      "algorithmic_bytes": fold_bytes, "kernel_ms": fold_ms, "peak_source": peak_src,
                      "round2_launch_GBps": r2, "round1_kernel_GBps": r1,
                      "whole_proof_vs_8TBps_nominal": (32 * T * (4 * N - 6)) / (ms_step * 1e-3) / 8e12},
         "secondary_roofline": {"bound": "int32 multiply pipe (IMAD.WIDE, 32 lane-ops/clk/SM)", "unit": "G modmul-equivalents/s",
-                               "achieved_round2": (2 ** (nv - 2)) * (6 * 76 + 3 * 111 + 3 * 64) / 111.0 / (round_ms[1] * 1e-3) / 1e9,
+                               "achieved_round2": (2 ** (nv - 2)) * ((6 * 8 if n_tc else 6 * 76) + 3 * 111 + 3 * 64) / 111.0 / (round_ms[1] * 1e-3) / 1e9,
                                "peak_measured_standalone": 58.7, "note": "tools/microbench/montmul.cu; DESIGN.md section 3"},
         "e2e": {"value": fs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": T * N * 32,
                 "d2h_bytes_per_step": nv * (d + 1) * 32 * 2, "ms_per_step": ms_e2e},

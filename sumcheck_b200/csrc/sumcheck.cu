@@ -16,6 +16,7 @@
 #include "gkr_kernels.cuh"
 #include "tail_params.cuh"
 #include "tmap_host.h"
+#include "tma_round1.cuh"
 
 static_assert(sizeof(sc_blake2b512_rng) == sizeof(b2::State), "sc_blake2b512_rng must be layout-identical to b2::State");
 
@@ -95,6 +96,7 @@ struct sc_prover {
     // tc_buf_ok[c]: rounds reading buffer c may use the TMA + tensor-core fold kernel (tc_round.cuh)
     uint8_t* d_maps = nullptr;
     bool tc_buf_ok[3] = {false, false, false};
+    bool r1_ok = false;  // [3][T..2T): the pristine tables again with 64-row boxes, for round1_tma_kernel
     unsigned long long tc_min_pairs = 0;
     int cur = 0;  // which buffer holds the current tables: 0 = tab0, 1 = A, 2 = B
     cudaStream_t stream = nullptr;      // the stream work is issued on
@@ -141,6 +143,42 @@ cudaError_t launch_round(sc_prover* p, bool fold, const sck::RoundParams& rp) {
     p->launches++;
     if (fold) return sck::launch_fold_round(NPTS, grid, rp, p->stream);  // compact translation unit (tail.cu)
     sck::round_kernel<NPTS, false><<<grid, threads, 0, p->stream>>>(rp);
+    return cudaGetLastError();
+}
+
+// Round 1 on the TMA-staged kernel (tma_round1.cuh).  Resident CTAs per SM from the function attributes (registers,
+// shared memory): see tail.cu tc_prepare for why the occupancy API is not used.
+template <int NPTS>
+cudaError_t launch_round1_tma(sc_prover* p, const sck::RoundParams& rp) {
+    static bool ready_dev[64] = {};
+    static int blocks_dev[64] = {};
+    const int dev = p->device & 63;
+    if (!ready_dev[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(sck::round1_tma_kernel<NPTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sck::R1_DYN_SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(sck::round1_tma_kernel<NPTS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, sck::round1_tma_kernel<NPTS>);
+        if (e != cudaSuccess) return e;
+        int regs_sm = 0, smem_sm = 0;
+        cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, p->device);
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, p->device);
+        const int regs_cta = ((fa.numRegs + 7) / 8 * 8) * (int)sck::R1_THREADS;
+        const int smem_cta = (int)fa.sharedSizeBytes + (int)sck::R1_DYN_SMEM + 1024;
+        int blocks = regs_sm / regs_cta;
+        if (smem_sm / smem_cta < blocks) blocks = smem_sm / smem_cta;
+        if (blocks < 1) blocks = 1;
+        if (getenv("SC_DEBUG")) fprintf(stderr, "round1_tma_kernel<%d>: %d CTAs/SM (regs %d)\n", NPTS, blocks, fa.numRegs);
+        blocks_dev[dev] = blocks;
+        ready_dev[dev] = true;
+    }
+    const unsigned long long n_tiles = rp.n_pairs / sck::R1_THREADS;
+    unsigned long long cap = (unsigned long long)g_dev[p->device].sms * blocks_dev[dev];
+    if (cap > (unsigned long long)p->max_grid) cap = p->max_grid;
+    const int grid = (int)(n_tiles < cap ? n_tiles : cap);
+    p->launches++;
+    sck::round1_tma_kernel<NPTS><<<grid, sck::R1_THREADS, sck::R1_DYN_SMEM, p->stream>>>(rp);
     return cudaGetLastError();
 }
 
@@ -226,6 +264,16 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
         rp.host_flag = (direct && take == remaining) ? p->d_result + (size_t)(p->d + 1) * 16 : nullptr;
         rp.host_out = direct ? p->d_result : nullptr;
         cudaError_t e;
+        if (!fold && p->r1_ok && p->cur == 0 && take == p->d + 1 && rp.n_pairs >= p->tc_min_pairs) {
+            rp.tmaps = p->d_maps + (size_t)3 * p->T * sizeof(CUtensorMap);  // round 1, one launch: TMA-staged kernel
+            switch (take) {
+                case 1: e = launch_round1_tma<1>(p, rp); break;
+                case 2: e = launch_round1_tma<2>(p, rp); break;
+                case 3: e = launch_round1_tma<3>(p, rp); break;
+                case 4: e = launch_round1_tma<4>(p, rp); break;
+                default: e = launch_round1_tma<5>(p, rp); break;
+            }
+        } else
         switch (take) {
             case 1: e = launch_round<1>(p, fold, rp); break;
             case 2: e = launch_round<2>(p, fold, rp); break;
@@ -302,7 +350,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     const size_t oCoef = take((size_t)n_products * 32), oPart = take((size_t)p->max_grid * sck::MAX_NPTS * 32), oCnt = take(4);
     const size_t oEv = take((size_t)(d + 1) * 32), oCa = take((size_t)(d + 1) * 32), oLag = take((size_t)2 * (d + 1) * 32);
     const size_t oTe = take((size_t)nv * (d + 1) * 32), oTc = take((size_t)nv * 32), oSt = take(2 * sizeof(b2::State));
-    const size_t oMaps = take((size_t)3 * T * sizeof(CUtensorMap));
+    const size_t oMaps = take((size_t)4 * T * sizeof(CUtensorMap));
     TRY_P(cudaMalloc(&p->slabA, off));
     uint8_t* base = (uint8_t*)p->slabA;
     for (uint32_t j = 0; j < T; j++) {
@@ -321,7 +369,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
         const char* env = getenv("SC_TC_MIN_PAIRS");
         p->tc_min_pairs = env ? strtoull(env, nullptr, 10) : sck::tc_min_pairs();
         if (p->tc_min_pairs < 128) p->tc_min_pairs = 128;
-        std::vector<CUtensorMap> maps((size_t)3 * T);
+        std::vector<CUtensorMap> maps((size_t)4 * T);
         const size_t len[3] = {N, nA, nB};
         for (int c = 0; c < 3 && !getenv("SC_NO_TC"); c++) {
             const uint64_t rows = len[c] / 4;
@@ -331,6 +379,11 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
                 ok = tmaph::make_table_map(&maps[(size_t)c * T + j], tb, rows, 128);
             }
             p->tc_buf_ok[c] = ok;
+        }
+        if (!getenv("SC_NO_TC") && !getenv("SC_NO_TMA_R1")) {  // round 1 reads 64-byte pairs: 64-row boxes = 128 pairs per tile
+            bool ok = N / 4 >= sck::R1_TILE_ROWS;
+            for (uint32_t j = 0; j < T && ok; j++) ok = tmaph::make_table_map(&maps[(size_t)3 * T + j], p->tab0[j], N / 4, sck::R1_TILE_ROWS);
+            p->r1_ok = ok;
         }
         TRY_P(cudaMemcpyAsync(p->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, p->stream));
         TRY_P(cudaStreamSynchronize(p->stream));  // `maps` is pageable and goes out of scope

@@ -161,7 +161,7 @@ def bench_main(args, nv, d, T, METRIC, UNIT, field_sums, algorithmic_bytes, Cloc
                        "cache": f"per-GPU shard {T * n_loc * 32 / 2**20:.0f} MiB, re-read from HBM every step",
                        "round_ms_rank0": [round(float(x), 4) for x in round_ms], "ranks_agree": bool(agree.item())},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "kernel": "sck::round_kernel<3,true> on rank 0's shard (incl. the fused peer-memory exchange), sharded rounds aggregated",
+                         "kernel": "sck::round_tc_kernel<3> / round_kernel<3,true> on rank 0's shard (TMA + tcgen05.mma fold for rounds with >= 2^14 pairs per shard; incl. the fused peer-memory exchange), sharded rounds aggregated",
                          "peak_source": src},
             "e2e": {"value": fs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": T * n_loc * 32 * world,
                     "d2h_bytes_per_step": nv * (d + 1) * 32 * 2 * world, "ms_per_step": ms_e2e},
