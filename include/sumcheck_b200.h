@@ -128,6 +128,11 @@ uint64_t sc_prover_launch_count(const sc_prover *p);
  * SC_TC_MIN_PAIRS=<n> moves the threshold (tests use 128 to cover the path at small sizes). */
 uint64_t sc_prover_tc_round_count(const sc_prover *p);
 
+/* interpolate_uni_poly (src/ml_sumcheck/protocol/verifier.rs:139-251): the value at r of the polynomial of degree
+ * n_evals-1 through (j, evals[j]), j = 0..n_evals-1 (n_evals <= 33).  Host-side scalar arithmetic (no GPU needed); the
+ * same routine finishes every prover round: the device delivers the summed points and P(1) = P_prev(r) - P(0). */
+int sc_fr_interpolate(const uint64_t *evals, uint32_t n_evals, const uint64_t r[4], uint64_t out[4]);
+
 /* ------------------------------------------------------------------------------------------------------------
  * GKRRoundSumcheck (src/gkr_round_sumcheck/mod.rs).  f1: SparseMultilinearExtension over 3*dim variables as nnz
  * (index, value) pairs with unique indices (its BTreeMap); index bits are g | x | y, least significant first

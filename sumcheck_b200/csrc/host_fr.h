@@ -1,0 +1,144 @@
+// Scalar BLS12-381 Fr arithmetic on the HOST, for the O(d^2) per-round glue around the device sums — what
+// prove_round does after its parallel reduce (prover.rs:138-153) plus the P(1) = P_prev(r) - P(0) identity
+// (verifier.rs:109-114, interpolate_uni_poly at verifier.rs:139-251).  The device delivers the d (or d+1) raw sums of
+// a round; scaling by a deferred coefficient, the claim from the previous message and the canonical (serialised) form
+// are ~25 multiplications — 1 us here against ~7 us of dependent latency on a single GPU warp.  Not a CPU path for the
+// protocol: tables never come here.  4 x u64 limbs, Montgomery R = 2^256 — the layout of ark-ff's Fp<MontBackend<_,4>,4>.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace hfr {
+
+struct F {
+    uint64_t l[4];
+};
+
+static const uint64_t P[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
+static const uint64_t INV = 0xfffffffeffffffffULL;  // -p^-1 mod 2^64
+static const F ONE = {{0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL, 0x1824b159acc5056fULL}};  // R mod p
+static const F R2 = {{0xc999e990f3f29c6dULL, 0x2b6cedcb87925c23ULL, 0x05d314967254398fULL, 0x0748d9d99f59ff11ULL}};   // R^2 mod p
+
+inline bool geq_p(const uint64_t (&a)[4]) {
+    for (int i = 3; i >= 0; i--) {
+        if (a[i] > P[i]) return true;
+        if (a[i] < P[i]) return false;
+    }
+    return true;
+}
+inline void sub_p(uint64_t (&a)[4]) {
+    unsigned __int128 bw = 0;
+    for (int i = 0; i < 4; i++) {
+        unsigned __int128 d = (unsigned __int128)a[i] - P[i] - (uint64_t)bw;
+        a[i] = (uint64_t)d;
+        bw = (d >> 64) & 1;
+    }
+}
+inline F add(const F& a, const F& b) {
+    F r;
+    unsigned __int128 c = 0;
+    for (int i = 0; i < 4; i++) {
+        c += (unsigned __int128)a.l[i] + b.l[i];
+        r.l[i] = (uint64_t)c;
+        c >>= 64;
+    }
+    if (geq_p(r.l)) sub_p(r.l);  // a + b < 2p < 2^256: no carry out
+    return r;
+}
+inline F sub(const F& a, const F& b) {
+    F r;
+    unsigned __int128 bw = 0;
+    for (int i = 0; i < 4; i++) {
+        unsigned __int128 d = (unsigned __int128)a.l[i] - b.l[i] - (uint64_t)bw;
+        r.l[i] = (uint64_t)d;
+        bw = (d >> 64) & 1;
+    }
+    if (bw) {
+        unsigned __int128 c = 0;
+        for (int i = 0; i < 4; i++) {
+            c += (unsigned __int128)r.l[i] + P[i];
+            r.l[i] = (uint64_t)c;
+            c >>= 64;
+        }
+    }
+    return r;
+}
+// Montgomery product a*b*2^-256 mod p (CIOS, 64-bit digits)
+inline F mul(const F& a, const F& b) {
+    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        unsigned __int128 c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (unsigned __int128)a.l[j] * b.l[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (uint64_t)c;
+        t[5] = (uint64_t)(c >> 64);
+        const uint64_t m = t[0] * INV;
+        c = (unsigned __int128)m * P[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < 4; j++) {
+            c += (unsigned __int128)m * P[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (uint64_t)c;
+        t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    F r = {{t[0], t[1], t[2], t[3]}};
+    if (t[4] || geq_p(r.l)) sub_p(r.l);
+    return r;
+}
+inline F from_u64(uint64_t k) {
+    F raw = {{k, 0, 0, 0}};
+    return mul(raw, R2);
+}
+inline F to_canonical(const F& a) {  // the integer ark-serialize writes
+    F one_int = {{1, 0, 0, 0}};
+    return mul(a, one_int);
+}
+inline F inverse(const F& a) {  // a^(p-2)
+    static const uint64_t E[4] = {0xfffffffeffffffffULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
+    F acc = ONE;
+    for (int i = 255; i >= 0; i--) {
+        acc = mul(acc, acc);
+        if ((E[i >> 6] >> (i & 63)) & 1) acc = mul(acc, a);
+    }
+    return acc;
+}
+
+// Lagrange weights w_j = 1 / prod_{k != j} (j - k) for the nodes 0..d (cached per degree; d <= 32)
+inline const std::vector<F>& lagrange_weights(uint32_t d) {
+    static std::vector<F> cache[33];
+    std::vector<F>& w = cache[d];
+    if (w.empty()) {
+        w.resize(d + 1);
+        for (uint32_t j = 0; j <= d; j++) {
+            F den = ONE;
+            for (uint32_t k = 0; k <= d; k++)
+                if (k != j) den = mul(den, sub(from_u64(j), from_u64(k)));
+            w[j] = inverse(den);
+        }
+    }
+    return w;
+}
+
+// The value at r of the degree-d polynomial through (j, evals[j]), j = 0..d (interpolate_uni_poly, verifier.rs:139).
+inline F interpolate(const F* evals, uint32_t d, const F& r) {
+    const std::vector<F>& w = lagrange_weights(d);
+    F diff[33], pre[34], suf[34];
+    for (uint32_t k = 0; k <= d; k++) diff[k] = sub(r, from_u64(k));
+    pre[0] = ONE;
+    for (uint32_t k = 0; k <= d; k++) pre[k + 1] = mul(pre[k], diff[k]);
+    suf[d + 1] = ONE;
+    for (uint32_t k = d + 1; k-- > 0;) suf[k] = mul(suf[k + 1], diff[k]);
+    F acc = {{0, 0, 0, 0}};
+    for (uint32_t j = 0; j <= d; j++) acc = add(acc, mul(mul(evals[j], w[j]), mul(pre[j], suf[j + 1])));
+    return acc;
+}
+
+}  // namespace hfr

@@ -60,6 +60,9 @@ struct RoundParams {
     // TMA + tensor-core fold rounds (tc_round.cuh): [n_tables] CUtensorMap descriptors of tab_in (128-byte rows,
     // SWIZZLE_128B, 128-row boxes); null for the plain kernels
     const void* tmaps;
+    // Raw delivery: the last block writes only the NPTS summed points (Montgomery, unscaled) to host_out and raises the
+    // flag; the deferred coefficient, P(1) from the claim and the canonical forms are finished on the host (host_fr.h)
+    uint32_t raw_out;
 };
 
 // P_prev(r) by Lagrange interpolation through (j, prev[j]), j = 0..d — what the verifier computes at
@@ -411,6 +414,20 @@ __device__ __forceinline__ void finish_round(const RoundParams& p, fr::WideAcc (
     }
     if (threadIdx.x >= 32) return;
     if (p.peer_mail) exchange_partials<NPTS>(p, acc, s_red);
+    if (p.raw_out) {  // thread 0 holds the totals: one coalesced store of NPTS*8 words to mapped host memory, then the flag
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int t = 0; t < NPTS; t++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) s_red[t * 8 + i] = acc[t].l[i];
+        }
+        __syncwarp();
+        for (uint32_t w = threadIdx.x; w < (uint32_t)NPTS * 8; w += 32) p.host_out[w] = s_red[w];
+        __threadfence_system();
+        __syncwarp();
+        if (threadIdx.x == 0) *p.host_flag = p.seq;
+        return;
+    }
     // deferred coefficient, P(1) from the claim, both output forms; with a flag the message also goes to mapped host memory
     publish_round<NPTS>(p, acc, r, s_red, nullptr);
     if (threadIdx.x == 0 && p.host_flag) *p.host_flag = p.seq;

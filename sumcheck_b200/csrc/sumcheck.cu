@@ -16,6 +16,7 @@
 #include "gkr_kernels.cuh"
 #include "tail_params.cuh"
 #include "tmap_host.h"
+#include "host_fr.h"
 #include "tma_round1.cuh"
 
 static_assert(sizeof(sc_blake2b512_rng) == sizeof(b2::State), "sc_blake2b512_rng must be layout-identical to b2::State");
@@ -95,6 +96,7 @@ struct sc_prover {
     // TMA descriptors of every table in each of the three buffers (tab0, A, B): [3][T] CUtensorMap in device memory;
     // tc_buf_ok[c]: rounds reading buffer c may use the TMA + tensor-core fold kernel (tc_round.cuh)
     uint8_t* d_maps = nullptr;
+    std::vector<CUtensorMap> h_maps;  // staging copy (kept alive: uploaded asynchronously)
     bool tc_buf_ok[3] = {false, false, false};
     bool r1_ok = false;  // [3][T..2T): the pristine tables again with 64-row boxes, for round1_tma_kernel
     unsigned long long tc_min_pairs = 0;
@@ -105,6 +107,10 @@ struct sc_prover {
     std::vector<float> round_ms;
     bool timing = false;
     bool used_skip1 = false;  // last device round summed t = 0, 2, .., d only
+    // host_post: rounds deliver only their raw sums; coefficient, claim and canonical forms are finished on the host
+    bool host_post = false, raw_active = false;
+    uint32_t raw_npts = 0;
+    std::vector<uint64_t> h_prev;  // the previous round's ProverMsg (d+1 elements), for the claim
     bool direct_results = true;  // rounds deliver their message through mapped host memory + flag
     bool direct_active = false;  // ... and the round just issued did so
     bool exchange = false;       // sharded round: fuse the partial-sum exchange into the round kernel
@@ -225,6 +231,7 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
         rp.host_out = p->d_result;
         rp.seq = ++p->seq;
     }
+    p->raw_active = false;
     if (fold && p->d <= (uint32_t)sck::MAX_NPTS && p->d_lagrange) {
         // rounds >= 2: P(0) + P(1) = P_prev(r) (the verifier's check, verifier.rs:109), so only t = 0, 2, .., d are summed
         rp.skip1 = 1;
@@ -232,6 +239,11 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
         rp.t0 = 0;
         rp.write_fold = 1;
         if (direct) rp.host_flag = p->d_result + (size_t)(p->d + 1) * 16;
+        if (direct && p->host_post) {
+            rp.raw_out = 1;
+            p->raw_active = true;
+            p->raw_npts = p->d;
+        }
         cudaError_t e;
         if (p->tc_buf_ok[p->cur] && rp.n_pairs >= p->tc_min_pairs) {
             // large fold round: tables staged by TMA, fix_variables on the tensor cores (tc_round.cuh)
@@ -263,6 +275,11 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
         rp.write_fold = (t0 == 0) ? 1u : 0u;
         rp.host_flag = (direct && take == remaining) ? p->d_result + (size_t)(p->d + 1) * 16 : nullptr;
         rp.host_out = direct ? p->d_result : nullptr;
+        if (direct && p->host_post && take == p->d + 1) {  // the whole message in one launch: raw delivery
+            rp.raw_out = 1;
+            p->raw_active = true;
+            p->raw_npts = take;
+        }
         cudaError_t e;
         if (!fold && p->r1_ok && p->cur == 0 && take == p->d + 1 && rp.n_pairs >= p->tc_min_pairs) {
             rp.tmaps = p->d_maps + (size_t)3 * p->T * sizeof(CUtensorMap);  // round 1, one launch: TMA-staged kernel
@@ -369,7 +386,8 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
         const char* env = getenv("SC_TC_MIN_PAIRS");
         p->tc_min_pairs = env ? strtoull(env, nullptr, 10) : sck::tc_min_pairs();
         if (p->tc_min_pairs < 128) p->tc_min_pairs = 128;
-        std::vector<CUtensorMap> maps((size_t)4 * T);
+        std::vector<CUtensorMap>& maps = p->h_maps;
+        maps.resize((size_t)4 * T);
         const size_t len[3] = {N, nA, nB};
         for (int c = 0; c < 3 && !getenv("SC_NO_TC"); c++) {
             const uint64_t rows = len[c] / 4;
@@ -386,7 +404,6 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
             p->r1_ok = ok;
         }
         TRY_P(cudaMemcpyAsync(p->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, p->stream));
-        TRY_P(cudaStreamSynchronize(p->stream));  // `maps` is pageable and goes out of scope
     }
     TRY_P(cudaMemcpyAsync(p->d_ptr0, p->tab0.data(), T * sizeof(uint32_t*), cudaMemcpyHostToDevice, p->stream));
     TRY_P(cudaMemcpyAsync(p->d_ptrA, p->bufA.data(), T * sizeof(uint32_t*), cudaMemcpyHostToDevice, p->stream));
@@ -415,6 +432,9 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     p->h_canon = p->h_result + (size_t)(d + 1) * 8;
     p->h_tail = (uint32_t*)((uint8_t*)p->h_result + hRes);
     p->h_st = (b2::State*)((uint8_t*)p->h_result + hRes + hTail);
+    p->host_post = !getenv("SC_TAIL") && !getenv("SC_NO_HOST_POST");
+    p->h_prev.assign((size_t)(d + 1) * 4, 0);
+    if (p->h_coeffs.empty()) p->h_coeffs.assign(coeffs, coeffs + (size_t)n_products * 4);
     p->ev.assign(2 * (size_t)nv, nullptr);  // CUDA events are created on demand (sc_prover_set_timing)
     p->round_ms.assign(nv, 0.f);
     p->randomness.reserve((size_t)nv * 4);
@@ -425,6 +445,35 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
 }
 
 int sharded_round(sc_prover* p, const uint64_t* r);  // capi_multi.inc
+
+// Finish a round whose kernel delivered raw sums (RoundParams::raw_out) into w->h_result: scale by the deferred
+// coefficient of a single product (c * sum == sum of c * terms, exact), fill P(1) = P_prev(r) - P(0) when the launch
+// summed t = 0, 2, .., d only (the identity the verifier checks, verifier.rs:109), and produce the canonical integers
+// ark-serialize feeds the transcript.  Writes the message into p->h_evals / p->h_canon.
+void host_finish_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
+    const uint32_t d = p->d, ns = w->raw_npts;
+    hfr::F sums[8], out[8], coeff;
+    memcpy(sums, w->h_result, (size_t)ns * 32);
+    const bool scale = p->n_products == 1;
+    if (scale) memcpy(&coeff, p->h_coeffs.data(), 32);
+    auto fin = [&](const hfr::F& x) { return scale ? hfr::mul(x, coeff) : x; };
+    if (w->used_skip1) {  // sums hold P(0), P(2), .., P(d)
+        hfr::F rr, prev[8];
+        memcpy(&rr, r, 32);
+        memcpy(prev, p->h_prev.data(), (size_t)(d + 1) * 32);
+        const hfr::F claim = hfr::interpolate(prev, d, rr);
+        out[0] = fin(sums[0]);
+        out[1] = hfr::sub(claim, out[0]);
+        for (uint32_t t = 2; t <= d; t++) out[t] = fin(sums[t - 1]);
+    } else {
+        for (uint32_t t = 0; t <= d; t++) out[t] = fin(sums[t]);
+    }
+    for (uint32_t t = 0; t <= d; t++) {
+        const hfr::F c = hfr::to_canonical(out[t]);
+        memcpy(p->h_evals + (size_t)t * 8, &out[t], 32);
+        memcpy(p->h_canon + (size_t)t * 8, &c, 32);
+    }
+}
 
 // prove_round state machine (prover.rs:78-98) + device round + D2H of the d+1 results into the pinned buffers.
 int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
@@ -464,14 +513,22 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
             }
         }
         __sync_synchronize();
-        if (w != p) memcpy(p->h_result, w->h_result, (size_t)(p->d + 1) * 64);
+        if (w->raw_active) {
+            host_finish_round(p, w, r_or_null);
+        } else if (w != p) {
+            memcpy(p->h_result, w->h_result, (size_t)(p->d + 1) * 64);
+        }
+        memcpy(p->h_prev.data(), p->h_evals, (size_t)(p->d + 1) * 32);
         if (p->comm && comm_failed(p)) return fail(SC_ERR_COMM, "a peer GPU did not deliver its partial sums in time");
         return SC_OK;
     }
     const size_t bytes = (size_t)(p->d + 1) * 32;
     CUDA_TRY(cudaMemcpyAsync(p->h_evals, p->out_evals, bytes, cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaMemcpyAsync(p->h_canon, p->out_canon, bytes, cudaMemcpyDeviceToHost, p->stream));
-    if (sync_out) CUDA_TRY(cudaStreamSynchronize(p->stream));
+    if (sync_out) {
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        memcpy(p->h_prev.data(), p->h_evals, (size_t)(p->d + 1) * 32);
+    }
     return SC_OK;
 }
 
@@ -754,6 +811,17 @@ uint32_t sc_prover_round_times_ms(const sc_prover* p, float* out, uint32_t cap) 
 }
 uint64_t sc_prover_launch_count(const sc_prover* p) { return p->launches; }
 uint64_t sc_prover_tc_round_count(const sc_prover* p) { return p->tc_rounds; }
+
+int sc_fr_interpolate(const uint64_t* evals, uint32_t n_evals, const uint64_t r[4], uint64_t out[4]) {
+    if (n_evals == 0 || n_evals > 33) return fail(SC_ERR_BAD_INPUT, "n_evals = %u out of range (1..33)", n_evals);
+    std::vector<hfr::F> ev(n_evals);
+    memcpy(ev.data(), evals, (size_t)n_evals * 32);
+    hfr::F rr;
+    memcpy(&rr, r, 32);
+    const hfr::F v = hfr::interpolate(ev.data(), n_evals - 1, rr);
+    memcpy(out, &v, 32);
+    return SC_OK;
+}
 int sc_prover_set_timing(sc_prover* p, int enabled) {
     p->want_timing = enabled != 0;
     if (p->want_timing) {

@@ -76,3 +76,23 @@ def test_synth_generators_agree(orc):
     for seed in (0x5C0000, 0x5C0301, 1):
         a, b, c = synth_table(5000, seed), synth_table_fast(5000, seed), orc.synth_table(5000, seed)
         assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_host_interpolation_matches_the_model():
+    """sc_fr_interpolate (csrc/host_fr.h: the host-side scalar routine that finishes every prover round, P(1) =
+    P_prev(r) - P(0)) against the big-int model's interpolate_uni_poly for every degree the reference's tests reach."""
+    import random
+    from oracle import pymodel as pm
+    from sumcheck_b200 import capi
+    L = capi.lib()
+    rnd = random.Random(2024)
+    for n in list(range(1, 15)) + [33]:
+        for trial in range(4):
+            evals = [rnd.randrange(pm.P) for _ in range(n)]
+            r = [0, 1, pm.P - 1, rnd.randrange(pm.P)][trial] if n > 1 else rnd.randrange(pm.P)
+            ev = np.array([pm.to_mont_limbs(v) for v in evals], dtype=np.uint64).reshape(n, 4)
+            rr = np.array(pm.to_mont_limbs(r), dtype=np.uint64)
+            out = np.zeros(4, dtype=np.uint64)
+            assert L.sc_fr_interpolate(ev.ctypes.data_as(capi.U64P), n, rr.ctypes.data_as(capi.U64P), out.ctypes.data_as(capi.U64P)) == 0
+            assert pm.from_mont_limbs(out) == pm.interpolate(evals, r)
+    assert L.sc_fr_interpolate(None, 0, None, None) != 0
