@@ -327,6 +327,8 @@ __device__ __forceinline__ Fr wide_reduce(const WideAcc& w) {
     hi.l[0] = q[8];
     hi.l[1] = q[9];
     lo = reduce_once(reduce_once(lo));
+    // the two top limbs are zero unless several products were accumulated (each is < 2^510): small rounds skip a multiply
+    if ((q[8] | q[9]) == 0) return lo;
     return add(lo, mul(hi, R2()));
 }
 
