@@ -128,6 +128,11 @@ uint64_t sc_prover_launch_count(const sc_prover *p);
  * SC_TC_MIN_PAIRS=<n> moves the threshold (tests use 128 to cover the path at small sizes). */
 uint64_t sc_prover_tc_round_count(const sc_prover *p);
 
+/* Handles return their device slab (<= 256 MiB), pinned result block and stream to a small per-device cache that later
+ * handles reuse (allocation latency dominates small proofs such as the two phases of a GKR round).  This frees it;
+ * SC_NO_ALLOC_CACHE=1 disables caching. */
+void sc_release_cached_memory(void);
+
 /* interpolate_uni_poly (src/ml_sumcheck/protocol/verifier.rs:139-251): the value at r of the polynomial of degree
  * n_evals-1 through (j, evals[j]), j = 0..n_evals-1 (n_evals <= 33).  Host-side scalar arithmetic (no GPU needed); the
  * same routine finishes every prover round: the device delivers the summed points and P(1) = P_prev(r) - P(0). */

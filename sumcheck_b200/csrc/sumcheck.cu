@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -66,6 +67,86 @@ int ensure_device(int device) {
     return SC_OK;
 }
 
+// ---- allocation cache ---------------------------------------------------------------------------------------------
+// cudaMalloc / cudaHostAlloc / cudaStreamCreate cost 0.1-10 ms each and vary wildly from call to call (measured: a
+// dim-18 GKR proof, which creates two provers, took 8.6 to 75 ms end to end on the same box).  Handles therefore return
+// their device slab (up to 256 MiB), their pinned+mapped result block and their stream to a small per-device cache that
+// the next handle of a similar size reuses.  sc_release_cached_memory() empties it.
+struct CachedBlock {
+    void* p;
+    size_t bytes;
+};
+struct AllocCache {
+    std::vector<CachedBlock> dev, host;
+    std::vector<cudaStream_t> streams;
+};
+AllocCache g_cache[64];
+std::mutex g_cache_mu;
+constexpr size_t CACHE_MAX_BLOCK = (size_t)256 << 20;
+constexpr size_t CACHE_MAX_ENTRIES = 8;
+
+bool cache_take(std::vector<CachedBlock>& v, size_t bytes, void** out, size_t* got) {
+    size_t best = v.size();
+    for (size_t i = 0; i < v.size(); i++)
+        if (v[i].bytes >= bytes && v[i].bytes <= bytes + bytes / 2 + 4096 && (best == v.size() || v[i].bytes < v[best].bytes)) best = i;
+    if (best == v.size()) return false;
+    *out = v[best].p;
+    *got = v[best].bytes;
+    v.erase(v.begin() + best);
+    return true;
+}
+cudaError_t device_alloc(void** out, size_t bytes, size_t* got, int device) {
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (cache_take(g_cache[device & 63].dev, bytes, out, got)) return cudaSuccess;
+    }
+    *got = bytes;
+    return cudaMalloc(out, bytes ? bytes : 1);
+}
+void device_free(void* p, size_t bytes, int device) {
+    if (!p) return;
+    if (bytes <= CACHE_MAX_BLOCK && !getenv("SC_NO_ALLOC_CACHE")) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto& v = g_cache[device & 63].dev;
+        if (v.size() < CACHE_MAX_ENTRIES) { v.push_back({p, bytes}); return; }
+    }
+    cudaFree(p);
+}
+cudaError_t host_mapped_alloc(void** out, size_t bytes, size_t* got, int device) {
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        if (cache_take(g_cache[device & 63].host, bytes, out, got)) return cudaSuccess;
+    }
+    *got = bytes;
+    return cudaHostAlloc(out, bytes, cudaHostAllocMapped);
+}
+void host_mapped_free(void* p, size_t bytes, int device) {
+    if (!p) return;
+    if (!getenv("SC_NO_ALLOC_CACHE")) {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto& v = g_cache[device & 63].host;
+        if (v.size() < CACHE_MAX_ENTRIES) { v.push_back({p, bytes}); return; }
+    }
+    cudaFreeHost(p);
+}
+cudaError_t stream_acquire(cudaStream_t* out, int device) {
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto& v = g_cache[device & 63].streams;
+        if (!v.empty()) { *out = v.back(); v.pop_back(); return cudaSuccess; }
+    }
+    return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+}
+void stream_release(cudaStream_t s, int device) {  // the caller has synchronised it
+    if (!s) return;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        auto& v = g_cache[device & 63].streams;
+        if (v.size() < CACHE_MAX_ENTRIES && !getenv("SC_NO_ALLOC_CACHE")) { v.push_back(s); return; }
+    }
+    cudaStreamDestroy(s);
+}
+
 }  // namespace
 
 // ================================================================================================ prover handle
@@ -77,6 +158,7 @@ struct sc_prover {
     std::vector<uint64_t> randomness;  // ProverState.randomness, 4 u64 each
     std::vector<uint32_t*> tab0, bufA, bufB;  // per-table device pointers
     uint32_t *slab0 = nullptr, *slabA = nullptr, *slabB = nullptr;
+    size_t slab0_bytes = 0, slabA_bytes = 0, h_result_bytes = 0;  // as handed out by the allocation cache
     uint32_t** d_ptr0 = nullptr;  // device arrays of table pointers
     uint32_t** d_ptrA = nullptr;
     uint32_t** d_ptrB = nullptr;
@@ -338,7 +420,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
         cudaError_t e__ = (expr);                                                                          \
         if (e__ != cudaSuccess) return bail(fail(SC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__))); \
     } while (0)
-    TRY_P(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+    TRY_P(stream_acquire(&p->own_stream, device));
     p->stream = p->own_stream;
     const size_t elem = 32, N = p->N;
     const size_t nA = N / 2 ? N / 2 : 1, nB = N / 4 ? N / 4 : 1;
@@ -347,7 +429,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
         p->owns_tab0 = false;
         for (uint32_t j = 0; j < T; j++) p->tab0[j] = (uint32_t*)tables[j];
     } else {
-        TRY_P(cudaMalloc(&p->slab0, (size_t)T * N * elem));
+        TRY_P(device_alloc((void**)&p->slab0, (size_t)T * N * elem, &p->slab0_bytes, device));
         for (uint32_t j = 0; j < T; j++) {
             p->tab0[j] = p->slab0 + (size_t)j * N * 8;
             // deep copy of the caller's table (prover.rs:55-59); pageable or pinned source both work
@@ -368,7 +450,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     const size_t oEv = take((size_t)(d + 1) * 32), oCa = take((size_t)(d + 1) * 32), oLag = take((size_t)2 * (d + 1) * 32);
     const size_t oTe = take((size_t)nv * (d + 1) * 32), oTc = take((size_t)nv * 32), oSt = take(2 * sizeof(b2::State));
     const size_t oMaps = take((size_t)4 * T * sizeof(CUtensorMap));
-    TRY_P(cudaMalloc(&p->slabA, off));
+    TRY_P(device_alloc((void**)&p->slabA, off, &p->slabA_bytes, device));
     uint8_t* base = (uint8_t*)p->slabA;
     for (uint32_t j = 0; j < T; j++) {
         p->bufA[j] = (uint32_t*)(base + oA) + (size_t)j * nA * 8;
@@ -425,7 +507,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
         TRY_P(cudaGetLastError());
     }
     const size_t hRes = up((size_t)(d + 1) * 64 + 64), hTail = up((size_t)nv * (d + 2) * 32), hSt = up(2 * sizeof(b2::State));
-    TRY_P(cudaHostAlloc(&p->h_result, hRes + hTail + hSt, cudaHostAllocMapped));
+    TRY_P(host_mapped_alloc((void**)&p->h_result, hRes + hTail + hSt, &p->h_result_bytes, device));
     memset(p->h_result, 0, hRes);
     TRY_P(cudaHostGetDevicePointer((void**)&p->d_result, p->h_result, 0));
     p->h_evals = p->h_result;
@@ -673,11 +755,11 @@ void sc_prover_destroy(sc_prover* p) {
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->sub) { p->sub->stream = p->sub->own_stream; sc_prover_destroy(p->sub); cudaSetDevice(p->device); }
     cudaFree(p->d_gather); cudaFree(p->d_evals_g); cudaFree(p->d_canon_g); cudaFree(p->d_sub_tabs);
-    if (p->owns_tab0) cudaFree(p->slab0);
-    cudaFree(p->slabA);  // one slab: ping-pong tables and every small device array
-    if (p->h_result) cudaFreeHost(p->h_result);  // one pinned block: results, tail read-back, transcript state
+    if (p->owns_tab0) device_free(p->slab0, p->slab0_bytes, p->device);
+    device_free(p->slabA, p->slabA_bytes, p->device);  // one slab: ping-pong tables and every small device array
+    host_mapped_free(p->h_result, p->h_result_bytes, p->device);  // one pinned block: results, tail read-back, transcript state
     for (auto e : p->ev) if (e) cudaEventDestroy(e);
-    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    stream_release(p->own_stream, p->device);  // synchronised above
     delete p;
 }
 
@@ -811,6 +893,22 @@ uint32_t sc_prover_round_times_ms(const sc_prover* p, float* out, uint32_t cap) 
 }
 uint64_t sc_prover_launch_count(const sc_prover* p) { return p->launches; }
 uint64_t sc_prover_tc_round_count(const sc_prover* p) { return p->tc_rounds; }
+
+void sc_release_cached_memory(void) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < 64; d++) {
+        AllocCache& c = g_cache[d];
+        if (c.dev.empty() && c.host.empty() && c.streams.empty()) continue;
+        cudaSetDevice(d);
+        for (auto& b : c.dev) cudaFree(b.p);
+        for (auto& b : c.host) cudaFreeHost(b.p);
+        for (auto& st : c.streams) cudaStreamDestroy(st);
+        c.dev.clear(); c.host.clear(); c.streams.clear();
+    }
+    cudaSetDevice(cur);
+}
 
 int sc_fr_interpolate(const uint64_t* evals, uint32_t n_evals, const uint64_t r[4], uint64_t out[4]) {
     if (n_evals == 0 || n_evals > 33) return fail(SC_ERR_BAD_INPUT, "n_evals = %u out of range (1..33)", n_evals);

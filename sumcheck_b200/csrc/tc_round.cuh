@@ -20,6 +20,9 @@ namespace sck {
 #ifndef SC_TC_SLOTS
 #define SC_TC_SLOTS 3
 #endif
+#ifndef SC_TC_MIN_BLOCKS
+#define SC_TC_MIN_BLOCKS 3
+#endif
 constexpr uint32_t TC_SLOTS = SC_TC_SLOTS;
 constexpr uint32_t TC_THREADS = tcf::TILE_ROWS;
 constexpr uint32_t TC_TMEM_COLS = 2 * tcf::ACC_COLS;  // power of two >= 32
@@ -27,7 +30,7 @@ constexpr size_t TC_DYN_SMEM = (size_t)TC_SLOTS * tcf::TILE_BYTES + tcf::BMAT_BY
 constexpr unsigned long long TC_MIN_PAIRS = 1ull << 14;  // smaller rounds are latency-bound: plain kernel
 
 template <int NPTS>
-__global__ void __launch_bounds__(TC_THREADS, 3) round_tc_kernel(const RoundParams p) {
+__global__ void __launch_bounds__(TC_THREADS, SC_TC_MIN_BLOCKS) round_tc_kernel(const RoundParams p) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];  // [TC_SLOTS] tiles, then the constants matrix
     __shared__ uint32_t s_red[32 * NPTS * 8];
     __shared__ bool s_last;
