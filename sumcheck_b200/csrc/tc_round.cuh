@@ -20,6 +20,10 @@ namespace sck {
 #ifndef SC_TC_SLOTS
 #define SC_TC_SLOTS 3
 #endif
+#ifndef SC_TC_WIDE_NPTS
+#define SC_TC_WIDE_NPTS 4  // NPTS from which the kernel is built for 2 CTAs/SM (up to 255 registers) instead of 3 (168):
+                           // measured on config 4 (d = 4): 7.92 -> 7.22 ms; at degree 3 two CTAs are 10 % slower
+#endif
 #ifndef SC_TC_MIN_BLOCKS
 #define SC_TC_MIN_BLOCKS 3
 #endif
@@ -30,7 +34,7 @@ constexpr size_t TC_DYN_SMEM = (size_t)TC_SLOTS * tcf::TILE_BYTES + tcf::BMAT_BY
 constexpr unsigned long long TC_MIN_PAIRS = 1ull << 14;  // smaller rounds are latency-bound: plain kernel
 
 template <int NPTS>
-__global__ void __launch_bounds__(TC_THREADS, SC_TC_MIN_BLOCKS) round_tc_kernel(const RoundParams p) {
+__global__ void __launch_bounds__(TC_THREADS, (NPTS >= SC_TC_WIDE_NPTS ? 2 : SC_TC_MIN_BLOCKS)) round_tc_kernel(const RoundParams p) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];  // [TC_SLOTS] tiles, then the constants matrix
     __shared__ uint32_t s_red[32 * NPTS * 8];
     __shared__ bool s_last;

@@ -10,6 +10,9 @@
 
 namespace sck {
 
+#ifndef SC_R1_WIDE_NPTS
+#define SC_R1_WIDE_NPTS 5  // NPTS from which the kernel is built for 2 CTAs/SM (255 registers, no spills) instead of 3 (168)
+#endif
 constexpr uint32_t R1_SLOTS = 4;
 constexpr uint32_t R1_THREADS = 128;
 constexpr uint32_t R1_TILE_ROWS = 64;                       // 128-byte rows (two pairs each) per work item
@@ -17,7 +20,7 @@ constexpr uint32_t R1_TILE_BYTES = R1_TILE_ROWS * 128;      // 8 KiB
 constexpr size_t R1_DYN_SMEM = (size_t)R1_SLOTS * R1_TILE_BYTES;
 
 template <int NPTS>
-__global__ void __launch_bounds__(R1_THREADS, 3) round1_tma_kernel(const RoundParams p) {
+__global__ void __launch_bounds__(R1_THREADS, (NPTS >= SC_R1_WIDE_NPTS ? 2 : 3)) round1_tma_kernel(const RoundParams p) {
     extern __shared__ __align__(1024) uint8_t r1_smem[];
     __shared__ uint32_t s_red[32 * NPTS * 8];
     __shared__ bool s_last;
