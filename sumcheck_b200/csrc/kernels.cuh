@@ -63,6 +63,9 @@ struct RoundParams {
     // Raw delivery: the last block writes only the NPTS summed points (Montgomery, unscaled) to host_out and raises the
     // flag; the deferred coefficient, P(1) from the claim and the canonical forms are finished on the host (host_fr.h)
     uint32_t raw_out;
+    // [n_products] 1 where the product's coefficient has already been multiplied into one of its tables (prover_init
+    // pre-scales a table that only this product uses): the hot loop then skips the two coefficient multiplies per pair
+    const uint8_t* prod_scaled;
 };
 
 // P_prev(r) by Lagrange interpolation through (j, prev[j]), j = 0..d — what the verifier computes at
@@ -172,7 +175,7 @@ __device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, b
     Fr step = fr::sub(v1, v0);
     Fr cur = v0;
     for (uint32_t s = 0; s < p.t0; s++) cur = fr::add(cur, step);  // only for d+1 > MAX_NPTS
-    if (first && !p.defer_coeff) {  // c_k * prod_j(...): scale the first multiplicand's line once
+    if (first && !p.defer_coeff && !(p.prod_scaled && p.prod_scaled[k])) {  // c_k * prod_j(...): scale the first multiplicand's line once
         Fr c = fr::load(p.coeffs + 8 * k);
         cur = fr::mul(cur, c);
         step = fr::mul(step, c);

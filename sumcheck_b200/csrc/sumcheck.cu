@@ -207,6 +207,11 @@ struct sc_prover {
     uint32_t switch_round = 0;     // first global round run replicated
     uint32_t *d_gather = nullptr, *d_evals_g = nullptr, *d_canon_g = nullptr, *d_sub_tabs = nullptr;
     std::vector<uint64_t> h_coeffs;
+    // Pre-applied coefficients: h_scaled[k] = 1 when product k's coefficient lives in table scaled_table[k] (a table only
+    // that product uses, scaled once at prover_init / load_tables); sc_prover_table divides it out again on export.
+    std::vector<uint8_t> h_scaled;
+    std::vector<int> scaled_table;
+    uint8_t* d_scaled = nullptr;
     std::vector<uint32_t> h_offsets, h_indices;
 };
 
@@ -289,6 +294,7 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
     rp.prod_indices = p->d_indices;
     rp.prod_first = p->d_first;
     rp.coeffs = p->d_coeffs;
+    rp.prod_scaled = p->d_scaled;
     rp.n_products = p->n_products;
     rp.n_tables = p->T;
     rp.defer_coeff = (p->n_products == 1) ? 1u : 0u;
@@ -402,8 +408,11 @@ int validate_products(uint32_t n_tables, uint32_t n_products, const uint32_t* of
     return SC_OK;
 }
 
+int prescale_tables(sc_prover* p);
+
 int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* const* tables, bool tables_on_device,
-                  uint32_t n_products, const uint64_t* coeffs, const uint32_t* offsets, const uint32_t* indices, int device) {
+                  uint32_t n_products, const uint64_t* coeffs, const uint32_t* offsets, const uint32_t* indices, int device,
+                  const uint8_t* inherit_scaled = nullptr) {
     *out = nullptr;
     if (nv == 0) return fail(SC_ERR_PANIC_CONSTANT, "Attempt to prove a constant.");
     if (nv > 40) return fail(SC_ERR_BAD_INPUT, "nv = %u too large", nv);
@@ -450,6 +459,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     const size_t oEv = take((size_t)(d + 1) * 32), oCa = take((size_t)(d + 1) * 32), oLag = take((size_t)2 * (d + 1) * 32);
     const size_t oTe = take((size_t)nv * (d + 1) * 32), oTc = take((size_t)nv * 32), oSt = take(2 * sizeof(b2::State));
     const size_t oMaps = take((size_t)4 * T * sizeof(CUtensorMap));
+    const size_t oScaled = take(n_products);
     TRY_P(device_alloc((void**)&p->slabA, off, &p->slabA_bytes, device));
     uint8_t* base = (uint8_t*)p->slabA;
     for (uint32_t j = 0; j < T; j++) {
@@ -501,6 +511,33 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     TRY_P(cudaMemcpyAsync(p->d_first, first.data(), nnz, cudaMemcpyHostToDevice, p->stream));
     TRY_P(cudaMemcpyAsync(p->d_coeffs, coeffs, (size_t)n_products * 32, cudaMemcpyHostToDevice, p->stream));
     TRY_P(cudaMemsetAsync(p->d_counter, 0, sizeof(unsigned int), p->stream));
+    {
+        // Coefficient pre-scaling (several products only; a single product's coefficient is applied to the sums): pick for
+        // every product a table that nothing else uses and multiply OUR copy of it by the coefficient once.
+        p->h_scaled.assign(n_products, 0);
+        p->scaled_table.assign(n_products, -1);
+        if (p->h_coeffs.empty()) p->h_coeffs.assign(coeffs, coeffs + (size_t)n_products * 4);
+        if (inherit_scaled) {  // replicated sub-prover of a sharded proof: its tables were gathered from scaled shards
+            p->h_scaled.assign(inherit_scaled, inherit_scaled + n_products);
+        } else if (!tables_on_device && n_products > 1 && !getenv("SC_NO_PRESCALE")) {
+            std::vector<uint32_t> uses(T, 0);
+            for (uint32_t j = 0; j < nnz; j++) uses[indices[j]]++;
+            for (uint32_t k = 0; k < n_products; k++) {
+                const uint64_t* c = coeffs + (size_t)k * 4;
+                if ((c[0] | c[1] | c[2] | c[3]) == 0) continue;  // zero has no inverse to export the table with
+                for (uint32_t j = offsets[k]; j < offsets[k + 1]; j++)
+                    if (uses[indices[j]] == 1) { p->scaled_table[k] = (int)indices[j]; p->h_scaled[k] = 1; break; }
+            }
+        }
+        bool any = false;
+        for (uint8_t f : p->h_scaled) any = any || f;
+        if (any) {
+            p->d_scaled = base + oScaled;
+            TRY_P(cudaMemcpyAsync(p->d_scaled, p->h_scaled.data(), n_products, cudaMemcpyHostToDevice, p->stream));
+            int rc2 = prescale_tables(p);
+            if (rc2) return bail(rc2);
+        }
+    }
     if (d + 1 <= 32) {  // Lagrange weights for the P(1)-from-claim shortcut
         p->d_lagrange = (uint32_t*)(base + oLag);
         sck::lagrange_setup_kernel<<<1, 32, 0, p->stream>>>(d, p->d_lagrange);
@@ -516,13 +553,27 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     p->h_st = (b2::State*)((uint8_t*)p->h_result + hRes + hTail);
     p->host_post = !getenv("SC_TAIL") && !getenv("SC_NO_HOST_POST");
     p->h_prev.assign((size_t)(d + 1) * 4, 0);
-    if (p->h_coeffs.empty()) p->h_coeffs.assign(coeffs, coeffs + (size_t)n_products * 4);
     p->ev.assign(2 * (size_t)nv, nullptr);  // CUDA events are created on demand (sc_prover_set_timing)
     p->round_ms.assign(nv, 0.f);
     p->randomness.reserve((size_t)nv * 4);
     TRY_P(cudaStreamSynchronize(p->stream));  // uploads done: the caller may free/modify its buffers
 #undef TRY_P
     *out = p;
+    return SC_OK;
+}
+
+// tab0[scaled_table[k]] *= coeffs[k] for every pre-scaled product (after an upload of the pristine tables)
+int prescale_tables(sc_prover* p) {
+    if (!p->d_scaled || !p->owns_tab0) return SC_OK;
+    for (uint32_t k = 0; k < p->n_products; k++) {
+        const int j = p->scaled_table[k];
+        if (!p->h_scaled[k] || j < 0) continue;
+        unsigned long long need = (p->N + 127) / 128, cap = (unsigned long long)g_dev[p->device].sms * 16;
+        const int grid = (int)(need < cap ? need : cap);
+        sck::scale_kernel<<<grid < 1 ? 1 : grid, 128, 0, p->stream>>>(p->tab0[j], p->d_coeffs + (size_t)k * 8, p->N, p->tab0[j]);
+        CUDA_TRY(cudaGetLastError());
+        p->launches++;
+    }
     return SC_OK;
 }
 
@@ -633,6 +684,7 @@ int run_tail(sc_prover* p, b2::State* st, uint32_t first, const uint64_t* r, uin
     memset(&tp, 0, sizeof(tp));
     sck::RoundParams& rp = tp.rp;
     rp.prod_offsets = p->d_offsets; rp.prod_indices = p->d_indices; rp.prod_first = p->d_first; rp.coeffs = p->d_coeffs;
+    rp.prod_scaled = p->d_scaled;
     rp.n_products = p->n_products; rp.n_tables = p->T; rp.defer_coeff = (p->n_products == 1) ? 1u : 0u;
     rp.t0 = 0; rp.write_fold = 1; rp.skip1 = 1; rp.fix1 = 1; rp.degree = d;
     rp.prev_evals = p->d_evals;  // ProverMsg of round first-1 (host-driven)
@@ -777,6 +829,8 @@ int sc_prover_load_tables(sc_prover* p, const uint64_t* const* tables) {
     CUDA_TRY(cudaSetDevice(p->device));
     for (uint32_t j = 0; j < p->T; j++)
         CUDA_TRY(cudaMemcpyAsync(p->tab0[j], tables[j], p->N * 32, cudaMemcpyHostToDevice, p->stream));
+    int rc = prescale_tables(p);
+    if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     return sc_prover_reset(p);
 }
@@ -823,6 +877,28 @@ int sc_prover_table(const sc_prover* p, uint32_t j, uint64_t* out, uint64_t cap_
     if (cap_elems < len) return fail(SC_ERR_BAD_INPUT, "buffer too small: %llu < %llu", (unsigned long long)cap_elems, (unsigned long long)len);
     const uint32_t* src = p->cur == 0 ? p->tab0[j] : (p->cur == 1 ? p->bufA[j] : p->bufB[j]);
     CUDA_TRY(cudaSetDevice(p->device));
+    int scaled_by = -1;
+    for (uint32_t k = 0; k < p->n_products && k < p->scaled_table.size(); k++)
+        if (p->h_scaled[k] && p->scaled_table[k] == (int)j) scaled_by = (int)k;
+    if (scaled_by >= 0) {
+        // this table carries its product's coefficient (prescale_tables): the reference's table is ours / c — exact
+        hfr::F c, cinv;
+        memcpy(&c, p->h_coeffs.data() + (size_t)scaled_by * 4, 32);
+        cinv = hfr::inverse(c);
+        uint32_t* tmp = nullptr;
+        size_t got = 0;
+        CUDA_TRY(device_alloc((void**)&tmp, len * 32 + 32, &got, p->device));
+        CUDA_TRY(cudaMemcpyAsync(tmp + len * 8, &cinv, 32, cudaMemcpyHostToDevice, p->stream));
+        unsigned long long need = (len + 127) / 128, cap = (unsigned long long)g_dev[p->device].sms * 16;
+        const int grid = (int)(need < cap ? need : cap);
+        sck::scale_kernel<<<grid < 1 ? 1 : grid, 128, 0, p->stream>>>(src, tmp + len * 8, len, tmp);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, tmp, len * 32, cudaMemcpyDeviceToHost, p->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(p->stream);
+        device_free(tmp, got, p->device);
+        if (e != cudaSuccess) return fail(SC_ERR_CUDA, "table export: %s", cudaGetErrorString(e));
+        return SC_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(out, src, len * 32, cudaMemcpyDeviceToHost, p->stream));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     return SC_OK;
