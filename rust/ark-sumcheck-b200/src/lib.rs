@@ -74,6 +74,11 @@ extern "C" {
         indices: *const u32, device: c_int, evals_out: *mut u64, randomness_out: *mut u64,
     ) -> c_int;
     pub fn sc_serialize_proof(evals: *const u64, nv: u32, d: u32, out: *mut u8) -> usize;
+    pub fn sc_prover_launch_count(p: *const ScProver) -> u64;
+    pub fn sc_prover_tc_round_count(p: *const ScProver) -> u64;
+    pub fn sc_release_cached_memory();
+    /// `interpolate_uni_poly` (verifier.rs:139): host-side, no GPU needed
+    pub fn sc_fr_interpolate(evals: *const u64, n_evals: u32, r: *const u64, out: *mut u64) -> c_int;
     pub fn sc_gkr_initialize_phase_one(
         dim: u32, nnz: u64, f1_idx: *const u64, f1_val: *const u64, f3: *const u64, g: *const u64, device: c_int,
         h_g_out: *mut u64, f1g_idx_out: *mut u64, f1g_val_out: *mut u64, nnz_g_out: *mut u64,

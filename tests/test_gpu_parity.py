@@ -280,6 +280,49 @@ def test_reset_reproves_identically(orc):
     assert np.array_equal(outs[0], orc.ml_prove(orc.Poly(nv, tabs, prods))[0])
 
 
+def test_prescaled_coefficients_reload_and_export(orc):
+    """Several products: prover_init multiplies each coefficient into a table only that product uses (csrc/sumcheck.cu
+    prescale_tables).  The proof, the tables ProverState exposes after every round (coefficient divided out again) and a
+    re-proof after sc_prover_load_tables must all equal the oracle's; shared tables and a zero coefficient keep the
+    in-kernel scaling."""
+    nv = 9
+    rnd = random.Random(21)
+    tables = [[rnd.randrange(pm.P) for _ in range(1 << nv)] for _ in range(6)]
+    # product 0: private tables 0,1; product 1: private table 2 + shared 5; product 2: only shared tables (5, 5);
+    # product 3: zero coefficient with a private table 3; product 4: single private multiplicand 4
+    products = [(rnd.randrange(1, pm.P), [0, 1]), (rnd.randrange(1, pm.P), [5, 2]), (rnd.randrange(1, pm.P), [5, 5]), (0, [3, 5]),
+                (pm.P - 1, [4])]
+    poly, opoly = both_polys(orc, nv, tables, products)
+    got, _ = assert_same_proof(orc, poly, opoly)
+    st, ost = sc.IPForMLSumcheck.prover_init(poly), orc.Prover(opoly)
+    v_msg = None
+    for i in range(4):
+        m = sc.IPForMLSumcheck.prove_round(st, v_msg)
+        assert np.array_equal(m.evaluations, ost.prove_round(None if v_msg is None else v_msg.randomness))
+        for j, ft in enumerate(poly.flattened_ml_extensions):
+            k = next(k for k, t in enumerate(opoly.tables) if t is ft)
+            assert np.array_equal(st.table(j), ost.table(k))
+        v_msg = sc.VerifierMsg(limbs(rnd.randrange(pm.P)))
+    import ctypes as C
+    st.load_tables(poly.flattened_ml_extensions)      # fresh upload of the caller's (unscaled) tables: scaled again
+    ev = np.zeros_like(got)
+    rng = sc.Blake2b512Rng.setup()
+    assert sc.lib().sc_ml_prove(st._h, C.byref(rng.state), ev.ctypes.data_as(sc.capi.U64P), None) == 0
+    assert np.array_equal(ev, got)
+
+
+def test_allocation_cache_reuse_and_release(orc):
+    """Handles hand their slab / pinned block / stream to the next handle: stale contents must never leak into a proof."""
+    L = sc.lib()
+    for rep in range(3):
+        for nv in (7, 10, 7):
+            tabs = [orc.synth_table(1 << nv, 9100 + 17 * rep + j) for j in range(3)]
+            prods = [(orc.synth_table(1, 9200 + rep)[0], [0, 1, 2])]
+            proof = sc.MLSumcheck.prove(build_poly(nv, tabs, prods))      # create -> prove -> destroy
+            assert np.array_equal(np.stack([m.evaluations for m in proof]), orc.ml_prove(orc.Poly(nv, tabs, prods))[0])
+        L.sc_release_cached_memory()
+
+
 # ------------------------------------------------------------------------------------------- BASELINE.json sizes
 def synth_poly(orc, cfg, nv, n_products, m):
     """SURVEY §8d synthetic inputs: table j of config c uses seed 0x5C0000 + 0x100*c + j, coefficients 0x5C00FF + 0x100*c."""
