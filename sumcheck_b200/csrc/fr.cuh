@@ -138,8 +138,10 @@ __device__ __forceinline__ Fr sub(const Fr& a, const Fr& b) {
     return t;
 }
 
-// Montgomery product a*b*2^-256 mod p: 63 IMAD.WIDE for the product + 48 for the reduction.
-__device__ __forceinline__ Fr mul_impl(const Fr& a, const Fr& b) {
+// Montgomery product a*b*2^-256 mod p WITHOUT the final conditional subtraction: 63 IMAD.WIDE for the product + 48 for the
+// reduction.  For a < 2p and b < p the result is < p*(2p/2^256 + 1) < 1.91p < 2p: a value that is only multiplied again
+// (by a canonical operand) or fed to the lazy accumulator may stay in [0, 2p).
+__device__ __forceinline__ Fr mul_lazy_impl(const Fr& a, const Fr& b) {
     uint32_t ev[16], od[16];
     mul_wide_eo(ev, od, a.l, b.l);
     uint32_t c = redc_eo(ev, od);
@@ -166,8 +168,9 @@ __device__ __forceinline__ Fr mul_impl(const Fr& a, const Fr& b) {
         "addc.u32 %7, %7, 0;\n\t"
         : "+r"(t.l[0]), "+r"(t.l[1]), "+r"(t.l[2]), "+r"(t.l[3]), "+r"(t.l[4]), "+r"(t.l[5]), "+r"(t.l[6]), "+r"(t.l[7])
         : "r"(c));
-    return reduce_once(t);
+    return t;
 }
+__device__ __forceinline__ Fr mul_impl(const Fr& a, const Fr& b) { return reduce_once(mul_lazy_impl(a, b)); }
 
 
 // FR_COMPACT (latency-bound kernels such as the fused tail): ONE out-of-line copy of the multiplier, arguments by value
@@ -176,8 +179,11 @@ __device__ __forceinline__ Fr mul_impl(const Fr& a, const Fr& b) {
 #ifdef FR_COMPACT
 static __device__ __noinline__ Fr mul_outlined(Fr a, Fr b) { return mul_impl(a, b); }
 __device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) { return mul_outlined(a, b); }
+static __device__ __noinline__ Fr mul_lazy_outlined(Fr a, Fr b) { return mul_lazy_impl(a, b); }
+__device__ __forceinline__ Fr mul_lazy(const Fr& a, const Fr& b) { return mul_lazy_outlined(a, b); }
 #else
 __device__ __forceinline__ Fr mul(const Fr& a, const Fr& b) { return mul_impl(a, b); }
+__device__ __forceinline__ Fr mul_lazy(const Fr& a, const Fr& b) { return mul_lazy_impl(a, b); }
 #endif
 
 // ---- multiplication by the round's challenge (the fix_variables fold) --------------------------------------------

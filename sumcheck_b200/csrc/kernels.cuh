@@ -222,8 +222,13 @@ __device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, b
                 Fr m2 = fr::add(prod[t - 2], prod[t - 2]);
                 Fr m6 = fr::add(fr::add(m2, m2), m2);
                 prod[t] = fr::sub(fr::sub(s, m6), prod[t - 4]);
+            } else if (consecutive) {
+                prod[t] = fr::mul(prod[t], cur);  // canonical: the finite differences above add and subtract these
+                SC_NEXT_POINT(t)
             } else {
-                prod[t] = fr::mul(prod[t], cur);
+                // the running product is only ever multiplied again by a canonical operand or fed to the lazy
+                // accumulator, so it may stay in [0, 2p): no conditional subtraction (fr::mul_lazy)
+                prod[t] = fr::mul_lazy(prod[t], cur);
                 SC_NEXT_POINT(t)
             }
         }
