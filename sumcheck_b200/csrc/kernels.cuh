@@ -342,16 +342,20 @@ __device__ __forceinline__ void publish_round(const RoundParams& p, const Fr (&a
 #define SC_THREADS 128
 #endif
 constexpr int ROUND_THREADS = SC_THREADS;  // CTA size of round_kernel in this translation unit
-constexpr uint32_t MAIL_WORDS = 64;   // per (slot, rank): up to 6 points x 8 words, flag at word 48
-constexpr uint32_t MAIL_FLAG = 48;
+constexpr uint32_t MAIL_WORDS = 128;  // per (slot, rank): up to 6 points x 8 limbs, each as a {limb, sequence number} pair
 constexpr uint32_t MAIL_SLOTS = 64;
 
 // Executed by warp 0 of the last block; thread 0 holds this rank's NPTS partial sums.  All-to-all over NVLink peer
-// memory: lane g stores the partials into rank g's mailbox, fences, then raises the flag; lane g then waits for rank
-// g's flag in the local mailbox.  On return thread 0 holds the sums over all ranks (rank order: same on every rank).
+// memory with a flag-in-data protocol: every limb travels as ONE 8-byte store {limb, sequence number} into the
+// receiver's mailbox, so the receiver just polls each word until its sequence number matches — one NVLink one-way
+// latency, no system-scope fence, no separate flag write behind it.  (The first version stored the limbs, fenced, then
+// raised a flag: two dependent round trips per round.)  Mailbox slots rotate (MAIL_SLOTS) so a fast rank's next round
+// never lands on words a slow rank has yet to read.  On return thread 0 holds the sums over all ranks, added in rank
+// order (the same on every rank).
 template <int NPTS>
 __device__ __forceinline__ void exchange_partials(const RoundParams& p, Fr (&acc)[NPTS], uint32_t* scratch) {
     const uint32_t lane = threadIdx.x & 31, G = p.n_ranks;
+    constexpr uint32_t NW = NPTS * 8;
     if (lane == 0) {
 #pragma unroll
         for (int t = 0; t < NPTS; t++)
@@ -359,30 +363,42 @@ __device__ __forceinline__ void exchange_partials(const RoundParams& p, Fr (&acc
             for (int i = 0; i < 8; i++) scratch[t * 8 + i] = acc[t].l[i];
     }
     __syncwarp();
-    for (uint32_t g = lane; g < G; g += 32) {
-        volatile uint32_t* dst = p.peer_mail[g] + ((size_t)p.mail_slot * G + p.rank) * MAIL_WORDS;
-        for (int w = 0; w < NPTS * 8; w++) dst[w] = scratch[w];
-        __threadfence_system();
-        dst[MAIL_FLAG] = p.mail_seq;
-    }
-    const uint32_t* mine = p.peer_mail[p.rank] + (size_t)p.mail_slot * G * MAIL_WORDS;
-    for (uint32_t g = lane; g < G; g += 32) {
-        const volatile uint32_t* src = mine + (size_t)g * MAIL_WORDS;
-        const long long t0 = clock64();
-        while (src[MAIL_FLAG] != p.mail_seq) {
-            if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer died; report instead of hanging the GPU
-                *p.comm_error = 1;
-                break;
-            }
+    for (uint32_t w = lane; w < NW; w += 32) {
+        const uint32_t v = scratch[w];
+        for (uint32_t g = 0; g < G; g++) {
+            uint32_t* dst = p.peer_mail[g] + ((size_t)p.mail_slot * G + p.rank) * MAIL_WORDS + 2 * w;
+            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(v), "r"(p.mail_seq) : "memory");
         }
     }
-    __threadfence();
+    __syncwarp();
+    const uint32_t* mine = p.peer_mail[p.rank] + (size_t)p.mail_slot * G * MAIL_WORDS;
+    for (uint32_t w = lane; w < NW; w += 32) {
+        for (uint32_t g = 0; g < G; g++) {
+            const uint32_t* src = mine + (size_t)g * MAIL_WORDS + 2 * w;
+            uint32_t d, f;
+            const long long t0 = clock64();
+            for (;;) {
+                asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(d), "=r"(f) : "l"(src) : "memory");
+                if (f == p.mail_seq) break;
+                if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer died; report instead of hanging the GPU
+                    *p.comm_error = 1;
+                    break;
+                }
+            }
+            scratch[(g + 1) * NW + w] = d;  // rows 1..G: the ranks' partials (row 0 still holds this rank's own)
+        }
+    }
     __syncwarp();
     if (lane == 0) {
 #pragma unroll
         for (int t = 0; t < NPTS; t++) {
             Fr s = fr::zero();
-            for (uint32_t g = 0; g < G; g++) s = fr::add(s, load_cg(mine + (size_t)g * MAIL_WORDS + t * 8));
+            for (uint32_t g = 0; g < G; g++) {
+                Fr x;
+#pragma unroll
+                for (int i = 0; i < 8; i++) x.l[i] = scratch[(g + 1) * NW + t * 8 + i];
+                s = fr::add(s, x);
+            }
             acc[t] = s;
         }
     }
