@@ -5,12 +5,12 @@
 //   * the table tile (128 rows x 128 bytes = old[4b..4b+3] for 128 consecutive b) is copied HBM -> shared memory by TMA
 //     (cp.async.bulk.tensor, SWIZZLE_128B) into a ring of TC_SLOTS slots, TC_SLOTS work items ahead of its use — no
 //     thread waits on a global load (the plain kernel spent 20 % of its warp time in long-scoreboard stalls);
-//   * one thread issues 4 tcgen05.mma.kind::i8 per tile (bytes of the tile x the round's constants matrix) into one of
-//     two 64-column accumulators in tensor memory, one work item ahead;
+//   * one lane (the duty rotates over the four warps) issues 4 tcgen05.mma.kind::i8 per tile (bytes of the tile x the
+//     round's constants matrix) into one of two 64-column accumulators in tensor memory, one work item ahead;
 //   * thread t (= TMEM lane t = row t of the tile) reads its 2 x 32 column sums, carries/reduces them to the two field
 //     elements (tcf::columns_to_fr), stores them (the folded table, 64 B per thread) and feeds the product terms.
 // A work item is one (tile, CSR entry of ProverState.list_of_products) — so any list of products works, tables shared
-// between products are simply staged again.  The IMAD.WIDE work per pair at degree 3 drops from 981 to ~575.
+// between products are simply staged again.  The IMAD.WIDE work per pair at degree 3 drops from 981 to 573.
 #pragma once
 #include "kernels.cuh"
 #include "tc_fold.cuh"
