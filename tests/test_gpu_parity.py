@@ -236,6 +236,15 @@ def test_tensor_core_fold_rounds(orc, monkeypatch, nv, n_products, mult_range, s
     assert sc.lib().sc_ml_prove(st2._h, C.byref(rng.state), ev2.ctypes.data_as(sc.capi.U64P), None) == 0
     assert st2.tc_round_count() == 0
     assert np.array_equal(ev2, ev)
+    # the message finished on the device (publish_round: coefficient, claim, canonical forms) instead of on the host
+    monkeypatch.delenv("SC_NO_TC")
+    monkeypatch.setenv("SC_NO_HOST_POST", "1")
+    st3 = sc.IPForMLSumcheck.prover_init(poly)
+    rng = sc.Blake2b512Rng.setup()
+    ev3 = np.zeros_like(ev)
+    assert sc.lib().sc_ml_prove(st3._h, C.byref(rng.state), ev3.ctypes.data_as(sc.capi.U64P), None) == 0
+    assert st3.tc_round_count() == want_tc
+    assert np.array_equal(ev3, ev)
 
 
 def test_tensor_core_fold_special_values_and_edge_challenges(orc, monkeypatch):
