@@ -74,7 +74,11 @@ void sc_prover_destroy(sc_prover *p);
 int sc_prover_reset(sc_prover *p);
 
 /* Replace the resident tables with new host data of the same shape (H2D into the pristine copies) and rewind to
- * round 0: the per-proof upload of a caller that proves many polynomials of one shape with one handle. */
+ * round 0: the per-proof upload of a caller that proves many polynomials of one shape with one handle.  For large
+ * single-product polynomials (nv >= 21, d + 1 <= 5) the upload is pipelined: the tables arrive in 8 chunks on a copy stream
+ * and round 1 — which needs no challenge — is summed chunk by chunk behind them, so the first prove_round / sc_ml_prove
+ * after this call finds its first message ready (sc_prover_reset discards it).  Returns when the caller's buffers may
+ * be reused.  SC_NO_EAGER_R1=1 disables the pipelining. */
 int sc_prover_load_tables(sc_prover *p, const uint64_t *const *tables);
 /* Run this handle's kernels and copies on the caller's CUDA stream (a cudaStream_t passed as void*; NULL restores
  * the handle's own stream), so the caller can order / time the work with its own events. */

@@ -66,6 +66,8 @@ struct RoundParams {
     // [n_products] 1 where the product's coefficient has already been multiplied into one of its tables (prover_init
     // pre-scales a table that only this product uses): the hot loop then skips the two coefficient multiplies per pair
     const uint8_t* prod_scaled;
+    // round1_tma_kernel on a sub-range of the tables (pipelined upload, sc_prover_load_tables): first 64-row tile
+    uint32_t tile_base;
 };
 
 // P_prev(r) by Lagrange interpolation through (j, prev[j]), j = 0..d — what the verifier computes at

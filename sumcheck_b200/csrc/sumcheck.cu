@@ -82,6 +82,8 @@ struct AllocCache {
 };
 AllocCache g_cache[64];
 std::mutex g_cache_mu;
+constexpr uint32_t EAGER_CHUNKS = 8;
+constexpr uint32_t EAGER_SLOT_WORDS = sck::MAX_NPTS * 8 + 8;  // raw sums, then the flag word
 constexpr size_t CACHE_MAX_BLOCK = (size_t)256 << 20;
 constexpr size_t CACHE_MAX_ENTRIES = 8;
 
@@ -191,6 +193,14 @@ struct sc_prover {
     bool used_skip1 = false;  // last device round summed t = 0, 2, .., d only
     // host_post: rounds deliver only their raw sums; coefficient, claim and canonical forms are finished on the host
     bool host_post = false, raw_active = false;
+    // Pipelined upload (sc_prover_load_tables): the tables arrive in EAGER_CHUNKS pieces on a copy stream while round 1 —
+    // which needs no challenge — is summed piece by piece behind them; the first prove_round then only adds the pieces up.
+    bool eager_valid = false;
+    uint32_t eager_epoch = 0;
+    uint32_t* h_eager = nullptr;   // pinned+mapped: [EAGER_CHUNKS][(MAX_NPTS * 8) sums + 8 (flag word first)]
+    uint32_t* d_eager = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t eager_ev[8] = {};
     uint32_t raw_npts = 0;
     std::vector<uint64_t> h_prev;  // the previous round's ProverMsg (d+1 elements), for the claim
     bool direct_results = true;  // rounds deliver their message through mapped host memory + flag
@@ -544,13 +554,17 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
         TRY_P(cudaGetLastError());
     }
     const size_t hRes = up((size_t)(d + 1) * 64 + 64), hTail = up((size_t)nv * (d + 2) * 32), hSt = up(2 * sizeof(b2::State));
-    TRY_P(host_mapped_alloc((void**)&p->h_result, hRes + hTail + hSt, &p->h_result_bytes, device));
+    const size_t hEager = up((size_t)EAGER_CHUNKS * EAGER_SLOT_WORDS * 4);
+    TRY_P(host_mapped_alloc((void**)&p->h_result, hRes + hTail + hSt + hEager, &p->h_result_bytes, device));
     memset(p->h_result, 0, hRes);
     TRY_P(cudaHostGetDevicePointer((void**)&p->d_result, p->h_result, 0));
     p->h_evals = p->h_result;
     p->h_canon = p->h_result + (size_t)(d + 1) * 8;
     p->h_tail = (uint32_t*)((uint8_t*)p->h_result + hRes);
     p->h_st = (b2::State*)((uint8_t*)p->h_result + hRes + hTail);
+    p->h_eager = (uint32_t*)((uint8_t*)p->h_result + hRes + hTail + hSt);
+    p->d_eager = (uint32_t*)((uint8_t*)p->d_result + hRes + hTail + hSt);
+    memset(p->h_eager, 0, hEager);
     p->host_post = !getenv("SC_TAIL") && !getenv("SC_NO_HOST_POST");
     p->h_prev.assign((size_t)(d + 1) * 4, 0);
     p->ev.assign(2 * (size_t)nv, nullptr);  // CUDA events are created on demand (sc_prover_set_timing)
@@ -623,6 +637,39 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
     if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1)], p->stream));
     // prover.rs:85-86: r = randomness[round-1] — the challenge just pushed
     int rc;
+    if (p->eager_valid && p->round == 1 && !p->comm) {
+        // round 1 was summed in EAGER_CHUNKS pieces behind the upload: wait for the last piece, add the pieces, finish
+        p->eager_valid = false;
+        volatile uint32_t* flag = p->h_eager + (size_t)(EAGER_CHUNKS - 1) * EAGER_SLOT_WORDS + sck::MAX_NPTS * 8;
+        unsigned long long spins = 0;
+        while (*flag != p->eager_epoch) {
+            if ((++spins & 0xfffff) == 0) {
+                cudaError_t q = cudaStreamQuery(p->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return fail(SC_ERR_CUDA, "round-1 chunk kernel failed: %s", cudaGetErrorString(q));
+                if (q == cudaSuccess && *flag != p->eager_epoch) return fail(SC_ERR_CUDA, "round-1 chunks finished without publishing");
+            }
+        }
+        __sync_synchronize();
+        const uint32_t npts = p->d + 1;
+        hfr::F tot[8];
+        memset(tot, 0, sizeof(tot));
+        for (uint32_t c = 0; c < EAGER_CHUNKS; c++)
+            for (uint32_t t = 0; t < npts; t++) {
+                hfr::F x;
+                memcpy(&x, p->h_eager + (size_t)c * EAGER_SLOT_WORDS + t * 8, 32);
+                tot[t] = hfr::add(tot[t], x);
+            }
+        memcpy(p->h_result, tot, (size_t)npts * 32);
+        p->raw_npts = npts;
+        p->used_skip1 = false;
+        host_finish_round(p, p, nullptr);
+        memcpy(p->h_prev.data(), p->h_evals, (size_t)npts * 32);
+        p->out_evals = p->d_evals;
+        p->out_canon = p->d_canon;
+        p->direct_active = true;
+        if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));  // the round's work ran during the upload
+        return SC_OK;
+    }
     if (p->comm) {
         rc = sharded_round(p, r_or_null);
     } else {
@@ -811,6 +858,8 @@ void sc_prover_destroy(sc_prover* p) {
     device_free(p->slabA, p->slabA_bytes, p->device);  // one slab: ping-pong tables and every small device array
     host_mapped_free(p->h_result, p->h_result_bytes, p->device);  // one pinned block: results, tail read-back, transcript state
     for (auto e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->copy_stream) { cudaStreamSynchronize(p->copy_stream); stream_release(p->copy_stream, p->device); }
+    for (auto& e : p->eager_ev) if (e) cudaEventDestroy(e);
     stream_release(p->own_stream, p->device);  // synchronised above
     delete p;
 }
@@ -821,18 +870,69 @@ int sc_prover_reset(sc_prover* p) {
     p->randomness.clear();
     p->launches = 0;
     p->tc_rounds = 0;
+    p->eager_valid = false;  // a pre-computed first round belongs to the proof that follows its upload only
     return SC_OK;
 }
 
 int sc_prover_load_tables(sc_prover* p, const uint64_t* const* tables) {
     if (!p->owns_tab0) return fail(SC_ERR_BAD_INPUT, "handle was created over caller-owned device tables");
     CUDA_TRY(cudaSetDevice(p->device));
-    for (uint32_t j = 0; j < p->T; j++)
-        CUDA_TRY(cudaMemcpyAsync(p->tab0[j], tables[j], p->N * 32, cudaMemcpyHostToDevice, p->stream));
-    int rc = prescale_tables(p);
-    if (rc) return rc;
-    CUDA_TRY(cudaStreamSynchronize(p->stream));
-    return sc_prover_reset(p);
+    // Pipelined path: round 1 needs no challenge, so it is summed chunk by chunk behind the copies (the upload of 1.5 GiB
+    // takes ~29 ms over PCIe; the 1.1 ms of round 1 disappear behind it).  One product with a deferred coefficient only
+    // (pre-scaled tables would have to be scaled before they are summed), single GPU, d + 1 <= 5 points, host finishing.
+    const unsigned long long tiles = p->N / 256;  // 64-row tiles of round 1 (128 pairs each)
+    const bool eager = p->r1_ok && p->host_post && !p->comm && !p->d_scaled && p->n_products == 1 && p->d + 1 <= (uint32_t)sck::MAX_NPTS &&
+                       tiles % EAGER_CHUNKS == 0 && tiles / EAGER_CHUNKS >= 1024 && !getenv("SC_NO_EAGER_R1");
+    if (!eager) {
+        for (uint32_t j = 0; j < p->T; j++)
+            CUDA_TRY(cudaMemcpyAsync(p->tab0[j], tables[j], p->N * 32, cudaMemcpyHostToDevice, p->stream));
+        int rc = prescale_tables(p);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        return sc_prover_reset(p);
+    }
+    if (!p->copy_stream) CUDA_TRY(stream_acquire(&p->copy_stream, p->device));
+    for (auto& e : p->eager_ev)
+        if (!e) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // the copies may only start once earlier work on the proving stream (a previous proof reading tab0) has finished
+    CUDA_TRY(cudaEventRecord(p->eager_ev[0], p->stream));
+    CUDA_TRY(cudaStreamWaitEvent(p->copy_stream, p->eager_ev[0], 0));
+    sc_prover_reset(p);
+    const uint32_t epoch = ++p->eager_epoch;
+    const size_t chunk_elems = p->N / EAGER_CHUNKS;
+    sck::RoundParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.tab_in = (const uint32_t* const*)p->d_ptr0;
+    rp.prod_offsets = p->d_offsets; rp.prod_indices = p->d_indices; rp.prod_first = p->d_first; rp.coeffs = p->d_coeffs;
+    rp.n_products = p->n_products; rp.n_tables = p->T; rp.defer_coeff = 1;
+    rp.n_pairs = chunk_elems / 2;
+    rp.partials = p->d_partials; rp.counter = p->d_counter;
+    rp.evals_out = p->d_evals; rp.canon_out = p->d_canon; rp.degree = p->d;
+    rp.tmaps = p->d_maps + (size_t)3 * p->T * sizeof(CUtensorMap);
+    rp.raw_out = 1;
+    rp.seq = epoch;
+    for (uint32_t c = 0; c < EAGER_CHUNKS; c++) {
+        for (uint32_t j = 0; j < p->T; j++)
+            CUDA_TRY(cudaMemcpyAsync(p->tab0[j] + c * chunk_elems * 8, tables[j] + c * chunk_elems * 4, chunk_elems * 32, cudaMemcpyHostToDevice,
+                                     p->copy_stream));
+        CUDA_TRY(cudaEventRecord(p->eager_ev[c], p->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(p->stream, p->eager_ev[c], 0));
+        rp.tile_base = (uint32_t)(c * (tiles / EAGER_CHUNKS));
+        rp.host_out = p->d_eager + (size_t)c * EAGER_SLOT_WORDS;
+        rp.host_flag = p->d_eager + (size_t)c * EAGER_SLOT_WORDS + sck::MAX_NPTS * 8;
+        cudaError_t e;
+        switch (p->d + 1) {
+            case 1: e = launch_round1_tma<1>(p, rp); break;
+            case 2: e = launch_round1_tma<2>(p, rp); break;
+            case 3: e = launch_round1_tma<3>(p, rp); break;
+            case 4: e = launch_round1_tma<4>(p, rp); break;
+            default: e = launch_round1_tma<5>(p, rp); break;
+        }
+        if (e != cudaSuccess) return fail(SC_ERR_CUDA, "round-1 chunk launch: %s", cudaGetErrorString(e));
+    }
+    CUDA_TRY(cudaStreamSynchronize(p->copy_stream));  // the caller's buffers are free again; the last chunk's sum may still run
+    p->eager_valid = true;
+    return SC_OK;
 }
 
 int sc_prover_set_stream(sc_prover* p, void* cuda_stream) {

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(R1_THREADS, (NPTS >= SC_R1_WIDE_NPTS ? 2 : 3))
     const uint32_t row = tid >> 1, half = tid & 1u;
     const uint32_t row_off = row * 128u, sw = row & 7u;
 
-    uint32_t tma_q = 0, tma_tile = blockIdx.x, tma_jj = 0;  // next item to stage (all threads track the cursors)
+    uint32_t tma_q = 0, tma_tile = p.tile_base + blockIdx.x, tma_jj = 0;  // next item to stage (all threads track the cursors)
     auto issue_tma = [&]() {
         if (lane == 0 && warp == (tma_q & 3u)) {
             const uint32_t slot = tma_q % R1_SLOTS;

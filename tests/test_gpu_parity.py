@@ -332,6 +332,32 @@ def test_allocation_cache_reuse_and_release(orc):
         L.sc_release_cached_memory()
 
 
+def test_pipelined_upload_first_round(orc):
+    """sc_prover_load_tables at nv >= 21: chunked H2D on a copy stream with round 1 summed chunk by chunk behind it.  The
+    proof after the upload, a proof after reset (round 1 recomputed normally) and the oracle must agree — on the NEW tables."""
+    import ctypes as C
+    nv = 21
+    old = [orc.synth_table(1 << nv, 31000 + j) for j in range(3)]
+    new = [orc.synth_table(1 << nv, 32000 + j) for j in range(3)]
+    coeff = orc.synth_table(1, 33000)[0]
+    st = sc.IPForMLSumcheck.prover_init(build_poly(nv, old, [(coeff, [0, 1, 2])]))
+    orc.set_threads(os.cpu_count() or 1)
+    try:
+        want = orc.ml_prove(orc.Poly(nv, new, [(coeff, [0, 1, 2])]))[0]
+    finally:
+        orc.set_threads(1)
+    for rep in range(2):
+        st.load_tables(new)
+        ev = np.zeros((nv, 4, 4), dtype=np.uint64)
+        st.prove_into(sc.Blake2b512Rng.setup(), ev)
+        assert np.array_equal(ev, want)
+        assert st.launch_count() == 8 + nv - 1          # 8 chunk launches of round 1, then one launch per round
+    st.reset()
+    ev2 = np.zeros_like(ev)
+    st.prove_into(sc.Blake2b512Rng.setup(), ev2)
+    assert np.array_equal(ev2, want) and st.launch_count() == nv
+
+
 # ------------------------------------------------------------------------------------------- BASELINE.json sizes
 def synth_poly(orc, cfg, nv, n_products, m):
     """SURVEY §8d synthetic inputs: table j of config c uses seed 0x5C0000 + 0x100*c + j, coefficients 0x5C00FF + 0x100*c."""
