@@ -7,6 +7,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 namespace hfr {
@@ -114,15 +115,18 @@ inline F inverse(const F& a) {  // a^(p-2)
 // Lagrange weights w_j = 1 / prod_{k != j} (j - k) for the nodes 0..d (cached per degree; d <= 32)
 inline const std::vector<F>& lagrange_weights(uint32_t d) {
     static std::vector<F> cache[33];
+    static std::mutex mu;  // handles may live on different host threads
+    std::lock_guard<std::mutex> lk(mu);
     std::vector<F>& w = cache[d];
     if (w.empty()) {
-        w.resize(d + 1);
+        std::vector<F> fresh(d + 1);
         for (uint32_t j = 0; j <= d; j++) {
             F den = ONE;
             for (uint32_t k = 0; k <= d; k++)
                 if (k != j) den = mul(den, sub(from_u64(j), from_u64(k)));
-            w[j] = inverse(den);
+            fresh[j] = inverse(den);
         }
+        w.swap(fresh);
     }
     return w;
 }

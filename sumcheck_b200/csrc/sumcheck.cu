@@ -87,6 +87,11 @@ constexpr uint32_t EAGER_SLOT_WORDS = sck::MAX_NPTS * 8 + 8;  // raw sums, then 
 constexpr size_t CACHE_MAX_BLOCK = (size_t)256 << 20;
 constexpr size_t CACHE_MAX_ENTRIES = 8;
 
+bool cache_enabled() {
+    static const bool on = !getenv("SC_NO_ALLOC_CACHE");
+    return on;
+}
+
 bool cache_take(std::vector<CachedBlock>& v, size_t bytes, void** out, size_t* got) {
     size_t best = v.size();
     for (size_t i = 0; i < v.size(); i++)
@@ -107,7 +112,7 @@ cudaError_t device_alloc(void** out, size_t bytes, size_t* got, int device) {
 }
 void device_free(void* p, size_t bytes, int device) {
     if (!p) return;
-    if (bytes <= CACHE_MAX_BLOCK && !getenv("SC_NO_ALLOC_CACHE")) {
+    if (bytes <= CACHE_MAX_BLOCK && cache_enabled()) {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto& v = g_cache[device & 63].dev;
         if (v.size() < CACHE_MAX_ENTRIES) { v.push_back({p, bytes}); return; }
@@ -124,7 +129,7 @@ cudaError_t host_mapped_alloc(void** out, size_t bytes, size_t* got, int device)
 }
 void host_mapped_free(void* p, size_t bytes, int device) {
     if (!p) return;
-    if (!getenv("SC_NO_ALLOC_CACHE")) {
+    if (cache_enabled()) {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto& v = g_cache[device & 63].host;
         if (v.size() < CACHE_MAX_ENTRIES) { v.push_back({p, bytes}); return; }
@@ -144,7 +149,7 @@ void stream_release(cudaStream_t s, int device) {  // the caller has synchronise
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto& v = g_cache[device & 63].streams;
-        if (v.size() < CACHE_MAX_ENTRIES && !getenv("SC_NO_ALLOC_CACHE")) { v.push_back(s); return; }
+        if (v.size() < CACHE_MAX_ENTRIES && cache_enabled()) { v.push_back(s); return; }
     }
     cudaStreamDestroy(s);
 }
