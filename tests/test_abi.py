@@ -96,3 +96,33 @@ def test_host_interpolation_matches_the_model():
             assert L.sc_fr_interpolate(ev.ctypes.data_as(capi.U64P), n, rr.ctypes.data_as(capi.U64P), out.ctypes.data_as(capi.U64P)) == 0
             assert pm.from_mont_limbs(out) == pm.interpolate(evals, r)
     assert L.sc_fr_interpolate(None, 0, None, None) != 0
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/sumcheck_b200.h is the drop-in boundary: it must compile as C99 and as C++, and a C program must link against
+    the shared library (entry points that need no GPU are called; without a device the compute ones fail loudly)."""
+    import shutil
+    import subprocess
+    from sumcheck_b200 import capi
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "use.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "sumcheck_b200.h"\n'
+        "int main(void) {\n"
+        "  sc_blake2b512_rng rng; unsigned char out[8]; uint64_t fr[4];\n"
+        "  sc_rng_setup(&rng); sc_rng_feed_bytes(&rng, (const uint8_t*)\"abc\", 3); sc_rng_fill_bytes(&rng, out, 8);\n"
+        "  sc_rng_sample_fr(&rng, fr);\n"
+        "  uint64_t evals[8] = {1,0,0,0, 2,0,0,0}, r[4] = {0,0,0,0}, v[4];\n"
+        "  if (sc_fr_interpolate(evals, 2, r, v) != 0) return 2;\n"
+        "  if (memcmp(v, evals, 32) != 0) return 3;   /* the interpolant at 0 is evals[0] */\n"
+        "  printf(\"%d\\n\", sc_device_count() >= 0 ? 0 : 1);\n"
+        "  return 0;\n}\n")
+    inc = os.path.join(ROOT, "include")
+    exe = tmp_path / "use"
+    lib = capi.lib_path()
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe), lib,
+                           "-Wl,-rpath," + os.path.dirname(lib)])
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", "-I", inc, str(src)])
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
