@@ -122,7 +122,7 @@ def main():
         from sumcheck_b200 import multi
         return multi.bench_main(args, nv, d, T, METRIC, UNIT, field_sums, algorithmic_bytes, ClockSampler)
 
-    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    args.warmup = max(args.warmup, 3)  # timing rules: at least 3 warm-up steps, whatever was asked for
     dev = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(dev)
     N = 1 << nv
