@@ -23,18 +23,35 @@ __device__ __forceinline__ Fr fr_R2() {  // R^2 mod p: mul(x, R2) = x*R mod p
     return r;
 }
 
-// eq[b] = prod_j (b_j ? g_j : 1 - g_j)  — ark-poly precompute_eq (external), bit j of b <-> g[j]
-__global__ void __launch_bounds__(128) eq_table_kernel(const uint32_t* g, uint32_t dim, uint32_t* out) {
-    const unsigned long long n = 1ull << dim;
+// eq[b] = prod_j (b_j ? g_j : 1 - g_j)  — ark-poly precompute_eq (external), bit j of b <-> g[j].
+// Two steps instead of dim multiplies per entry (the first version: O(N*dim)): the factors of the low
+// `lo` variables and of the high dim-lo variables are tabulated separately (2^lo + 2^(dim-lo) short products), then
+// eq[b] = eq_lo[b & (2^lo - 1)] * eq_hi[b >> lo] — one multiply per entry.  Same factors, exact arithmetic: same element.
+__device__ __forceinline__ Fr eq_partial(const uint32_t* g, uint32_t first, uint32_t count, unsigned long long b) {
+    Fr acc = fr::one();
+    for (uint32_t j = 0; j < count; j++) {
+        Fr gj = fr::load(g + 8 * (first + j));
+        Fr f = ((b >> j) & 1) ? gj : fr::sub(fr::one(), gj);
+        acc = (j == 0) ? f : fr::mul(acc, f);
+    }
+    return acc;
+}
+// halves[0 .. 2^lo) = eq over g[0..lo), halves[2^lo .. 2^lo + 2^(dim-lo)) = eq over g[lo..dim)
+__global__ void __launch_bounds__(128) eq_halves_kernel(const uint32_t* g, uint32_t dim, uint32_t lo, uint32_t* halves) {
+    const unsigned long long n_lo = 1ull << lo, n_hi = 1ull << (dim - lo);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_lo + n_hi;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const Fr v = i < n_lo ? eq_partial(g, 0, lo, i) : eq_partial(g, lo, dim - lo, i - n_lo);
+        fr::store(halves + i * 8, v);
+    }
+}
+__global__ void __launch_bounds__(128) eq_outer_kernel(const uint32_t* halves, uint32_t dim, uint32_t lo, uint32_t* out) {
+    const unsigned long long n = 1ull << dim, n_lo = 1ull << lo;
     for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < n;
          b += (unsigned long long)gridDim.x * blockDim.x) {
-        Fr acc = fr::one();
-        for (uint32_t j = 0; j < dim; j++) {
-            Fr gj = fr::load(g + 8 * j);
-            Fr f = ((b >> j) & 1) ? gj : fr::sub(fr::one(), gj);
-            acc = (j == 0) ? f : fr::mul(acc, f);
-        }
-        fr::store(out + b * 8, acc);
+        const Fr a = fr::load(halves + (b & (n_lo - 1)) * 8);
+        if (lo == dim) { fr::store(out + b * 8, a); continue; }
+        fr::store(out + b * 8, fr::mul(a, fr::load(halves + (n_lo + (b >> lo)) * 8)));
     }
 }
 

@@ -55,6 +55,7 @@ struct RoundParams {
     uint32_t* const* peer_mail;     // [n_ranks] mailbox base of every rank as mapped in THIS process; null = single GPU
     uint32_t n_ranks, rank, mail_slot, mail_seq;
     uint32_t* comm_error;           // mapped host word set to 1 when a peer does not answer in time
+    long long mail_timeout;         // clock64 ticks to wait for a peer (SC_COMM_TIMEOUT_S, default 30 s)
     const uint32_t* prev_evals;     // [(d+1)][8] previous round's ProverMsg (may alias evals_out: read first)
     const uint32_t* lagrange;       // [2][(d+1)][8]: w_j = 1/prod_{k!=j}(j-k), then the field elements 0..d
     // TMA + tensor-core fold rounds (tc_round.cuh): [n_tables] CUtensorMap descriptors of tab_in (128-byte rows,
@@ -347,10 +348,26 @@ constexpr int ROUND_THREADS = SC_THREADS;  // CTA size of round_kernel in this t
 constexpr uint32_t MAIL_WORDS = 128;  // per (slot, rank): up to 6 points x 8 limbs, each as a {limb, sequence number} pair
 constexpr uint32_t MAIL_SLOTS = 64;
 
+// One mailbox word = {limb, sequence number} packed into ONE 64-bit register and moved with a scalar 8-byte access.  The
+// PTX memory model guarantees single-copy atomicity for naturally aligned scalar accesses up to 64 bits (a .v2.u32 access
+// is two 32-bit accesses in unspecified order and gives no such guarantee), so a reader that sees the new sequence number
+// sees the limb that was stored with it.  relaxed.sys: the word may live in a peer GPU's memory or in mapped host memory.
+__device__ __forceinline__ void mail_store(uint32_t* dst, uint32_t value, uint32_t seq) {
+    const unsigned long long w = (unsigned long long)value | ((unsigned long long)seq << 32);
+    asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(dst), "l"(w) : "memory");
+}
+__device__ __forceinline__ void mail_load(const uint32_t* src, uint32_t& value, uint32_t& seq) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+    value = (uint32_t)w;
+    seq = (uint32_t)(w >> 32);
+}
+
 // Executed by warp 0 of the last block; thread 0 holds this rank's NPTS partial sums.  All-to-all over NVLink peer
 // memory with a flag-in-data protocol: every limb travels as ONE 8-byte store {limb, sequence number} into the
 // receiver's mailbox, so the receiver just polls each word until its sequence number matches — one NVLink one-way
-// latency, no system-scope fence, no separate flag write behind it.  (The first version stored the limbs, fenced, then
+// latency, no system-scope fence, no separate flag write behind it (mail_store/mail_load above: the 8 bytes are
+// single-copy atomic).  (The first version stored the limbs, fenced, then
 // raised a flag: two dependent round trips per round.)  Mailbox slots rotate (MAIL_SLOTS) so a fast rank's next round
 // never lands on words a slow rank has yet to read.  On return thread 0 holds the sums over all ranks, added in rank
 // order (the same on every rank).
@@ -369,7 +386,7 @@ __device__ __forceinline__ void exchange_partials(const RoundParams& p, Fr (&acc
         const uint32_t v = scratch[w];
         for (uint32_t g = 0; g < G; g++) {
             uint32_t* dst = p.peer_mail[g] + ((size_t)p.mail_slot * G + p.rank) * MAIL_WORDS + 2 * w;
-            asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(v), "r"(p.mail_seq) : "memory");
+            mail_store(dst, v, p.mail_seq);
         }
     }
     __syncwarp();
@@ -380,10 +397,11 @@ __device__ __forceinline__ void exchange_partials(const RoundParams& p, Fr (&acc
             uint32_t d, f;
             const long long t0 = clock64();
             for (;;) {
-                asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(d), "=r"(f) : "l"(src) : "memory");
+                mail_load(src, d, f);
                 if (f == p.mail_seq) break;
-                if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer died; report instead of hanging the GPU
+                if (clock64() - t0 > p.mail_timeout) {  // a peer died (default ~30 s): report instead of hanging the GPU
                     *p.comm_error = 1;
+                    d = 0;
                     break;
                 }
             }
@@ -478,31 +496,6 @@ __global__ void __launch_bounds__(SC_THREADS, SC_MIN_BLOCKS) round_kernel(const 
     accumulate_pairs<NPTS, FOLD, true>(p, s_foldC, (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x,
                                        (unsigned long long)gridDim.x * blockDim.x, accw);
     finish_round<NPTS>(p, accw, r, s_red, &s_last);
-}
-
-// Lagrange data for claim_from_prev: w_j = 1 / prod_{k != j} (j - k) and the field elements 0..d (one thread per j).
-static __global__ void lagrange_setup_kernel(uint32_t d, uint32_t* out) {
-    const uint32_t j = threadIdx.x;
-    if (j > d) return;
-    Fr r2 = {{0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u}};
-    Fr raw = fr::zero();
-    raw.l[0] = j;
-    const Fr fj = fr::mul(raw, r2);  // j in Montgomery form
-    fr::store(out + (size_t)(d + 1 + j) * 8, fj);
-    Fr den = fr::one();
-    for (uint32_t k = 0; k <= d; k++) {
-        if (k == j) continue;
-        raw.l[0] = k;
-        den = fr::mul(den, fr::sub(fj, fr::mul(raw, r2)));
-    }
-    // den^(p-2) by square-and-multiply, p - 2 = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfefffffffeffffffff
-    const uint32_t e[8] = {0xffffffffu, 0xfffffffeu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
-    Fr acc = fr::one();
-    for (int i = 255; i >= 0; i--) {
-        acc = fr::mul(acc, acc);
-        if ((e[i >> 5] >> (i & 31)) & 1) acc = fr::mul(acc, den);
-    }
-    fr::store(out + (size_t)j * 8, acc);
 }
 
 }  // namespace sck

@@ -4,12 +4,17 @@
 // arithmetic runs on the device; there is no CPU fallback — without a CUDA device every entry point fails.
 #include <cuda_runtime.h>
 
+#include <sched.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#endif
 
 #include "../../include/sumcheck_b200.h"
 #include "blake2b.cuh"
@@ -42,11 +47,37 @@ int fail(int code, const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail(SC_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
 
+// Host-side wait for a word the GPU writes into mapped pinned memory.  The expected wait is a few microseconds (one
+// kernel), so the first polls only PAUSE (frees the sibling hyper-thread, keeps the store visible at once); a long wait
+// (a multi-millisecond round of a big proof, or a peer rank still uploading) backs off to sched_yield so that a caller
+// which also runs a rayon/OpenMP pool on the same cores is not starved (SURVEY §8b "threading").
+struct SpinWait {
+    unsigned long long n = 0;
+    inline void pause() {
+        ++n;
+        if (n < 2048) {
+#if defined(__x86_64__) || defined(__i386__)
+            _mm_pause();
+#elif defined(__aarch64__)
+            asm volatile("yield" ::: "memory");
+#endif
+        } else if (n < 65536) {
+#if defined(__x86_64__) || defined(__i386__)
+            for (int i = 0; i < 16; i++) _mm_pause();
+#endif
+        } else {
+            sched_yield();
+        }
+    }
+    inline bool check_now() const { return (n & 0xffff) == 0; }  // time to ask the driver whether the kernel died
+};
+
 struct DeviceInfo {
     bool ready = false;
     int sms = 0;
 };
 DeviceInfo g_dev[64];
+std::mutex g_dev_mu;  // one-time per-device initialisation (constants, attributes); handles may live on different threads
 
 int ensure_device(int device) {
     int n = 0;
@@ -55,6 +86,7 @@ int ensure_device(int device) {
         return fail(SC_ERR_NO_DEVICE, "no CUDA device (%s); sumcheck_b200 has no CPU path", cudaGetErrorString(e));
     if (device < 0 || device >= n || device >= 64) return fail(SC_ERR_BAD_INPUT, "device %d out of range (%d visible)", device, n);
     CUDA_TRY(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lk(g_dev_mu);
     if (!g_dev[device].ready) {
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -84,8 +116,18 @@ AllocCache g_cache[64];
 std::mutex g_cache_mu;
 constexpr uint32_t EAGER_CHUNKS = 8;
 constexpr uint32_t EAGER_SLOT_WORDS = sck::MAX_NPTS * 8 + 8;  // raw sums, then the flag word
-constexpr size_t CACHE_MAX_BLOCK = (size_t)256 << 20;
 constexpr size_t CACHE_MAX_ENTRIES = 8;
+// Largest block the cache keeps and the most it holds per device.  The nv = 24 one-shot proof (MLSumcheck::prove: create +
+// prove + destroy) allocates a 1.5 GiB and a 1.1 GiB slab: with the first-round limit of 256 MiB both went through
+// cudaMalloc/cudaFree on every call.  180 GB of HBM make 8 GiB of parked slabs cheap;
+// SC_CACHE_MAX_MB=<n> changes the budget, sc_release_cached_memory() returns everything.
+size_t cache_budget() {
+    static const size_t v = [] {
+        const char* e = getenv("SC_CACHE_MAX_MB");
+        return (size_t)(e ? strtoull(e, nullptr, 10) : 8192) << 20;
+    }();
+    return v;
+}
 
 bool cache_enabled() {
     static const bool on = !getenv("SC_NO_ALLOC_CACHE");
@@ -108,14 +150,22 @@ cudaError_t device_alloc(void** out, size_t bytes, size_t* got, int device) {
         if (cache_take(g_cache[device & 63].dev, bytes, out, got)) return cudaSuccess;
     }
     *got = bytes;
-    return cudaMalloc(out, bytes ? bytes : 1);
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e == cudaErrorMemoryAllocation) {  // parked slabs may be what is in the way: give them back and retry once
+        cudaGetLastError();
+        sc_release_cached_memory();
+        e = cudaMalloc(out, bytes ? bytes : 1);
+    }
+    return e;
 }
 void device_free(void* p, size_t bytes, int device) {
     if (!p) return;
-    if (bytes <= CACHE_MAX_BLOCK && cache_enabled()) {
+    if (cache_enabled()) {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto& v = g_cache[device & 63].dev;
-        if (v.size() < CACHE_MAX_ENTRIES) { v.push_back({p, bytes}); return; }
+        size_t held = 0;
+        for (auto& b : v) held += b.bytes;
+        if (v.size() < CACHE_MAX_ENTRIES && held + bytes <= cache_budget()) { v.push_back({p, bytes}); return; }
     }
     cudaFree(p);
 }
@@ -228,9 +278,25 @@ struct sc_prover {
     std::vector<int> scaled_table;
     uint8_t* d_scaled = nullptr;
     std::vector<uint32_t> h_offsets, h_indices;
+    std::vector<uint64_t> h_lagrange;  // staging copy of d_lagrange (uploaded asynchronously)
+    void* adopted = nullptr;           // a device block whose ownership was handed to this handle (freed on destroy)
+    size_t adopted_bytes = 0;
 };
 
 namespace {
+
+// [w_0..w_d | 0..d] as Montgomery elements: w_j = 1 / prod_{k != j} (j - k) (kernels.cuh claim_from_prev).  The first
+// version ran a 256-step square-and-multiply per lane on one warp at every prover_init (195 us).
+std::vector<uint64_t> lagrange_block(uint32_t d) {
+    const std::vector<hfr::F>& w = hfr::lagrange_weights(d);
+    std::vector<uint64_t> out((size_t)2 * (d + 1) * 4);
+    for (uint32_t j = 0; j <= d; j++) {
+        memcpy(&out[(size_t)j * 4], &w[j], 32);
+        const hfr::F fj = hfr::from_u64(j);
+        memcpy(&out[(size_t)(d + 1 + j) * 4], &fj, 32);
+    }
+    return out;
+}
 
 template <int NPTS>
 int occupancy_blocks_nofold() {
@@ -292,6 +358,7 @@ cudaError_t launch_round1_tma(sc_prover* p, const sck::RoundParams& rp) {
 
 void set_exchange_params(sc_prover* p, sck::RoundParams& rp);  // capi_multi.inc
 bool comm_failed(const sc_prover* p);
+void comm_clear_error(sc_prover* p);
 
 // One protocol round on the device: (fold on r) + sums for all d+1 points.  Results land in d_evals / d_canon.
 int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
@@ -411,6 +478,8 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
 
 int validate_products(uint32_t n_tables, uint32_t n_products, const uint32_t* offsets, const uint32_t* indices, uint32_t* d_out) {
     if (n_products == 0 || n_tables == 0) return fail(SC_ERR_BAD_INPUT, "empty polynomial");
+    if (!offsets || !indices) return fail(SC_ERR_BAD_INPUT, "null product list");
+    if (offsets[0] != 0) return fail(SC_ERR_BAD_INPUT, "offsets[0] must be 0 (got %u)", offsets[0]);
     uint32_t d = 0;
     for (uint32_t k = 0; k < n_products; k++) {
         if (offsets[k + 1] <= offsets[k]) return fail(SC_ERR_BAD_INPUT, "product %u is empty (data_structures.rs:78)", k);
@@ -428,8 +497,10 @@ int prescale_tables(sc_prover* p);
 int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* const* tables, bool tables_on_device,
                   uint32_t n_products, const uint64_t* coeffs, const uint32_t* offsets, const uint32_t* indices, int device,
                   const uint8_t* inherit_scaled = nullptr) {
+    if (!out) return fail(SC_ERR_BAD_INPUT, "null output handle");
     *out = nullptr;
     if (nv == 0) return fail(SC_ERR_PANIC_CONSTANT, "Attempt to prove a constant.");
+    if (!tables || !coeffs) return fail(SC_ERR_BAD_INPUT, "null tables or coefficients");
     if (nv > 40) return fail(SC_ERR_BAD_INPUT, "nv = %u too large", nv);
     uint32_t d = 0;
     int rc = validate_products(T, n_products, offsets, indices, &d);
@@ -553,10 +624,10 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
             if (rc2) return bail(rc2);
         }
     }
-    if (d + 1 <= 32) {  // Lagrange weights for the P(1)-from-claim shortcut
+    if (d + 1 <= 32) {  // Lagrange weights + the nodes 0..d for the P(1)-from-claim shortcut: host table (cached per degree)
         p->d_lagrange = (uint32_t*)(base + oLag);
-        sck::lagrange_setup_kernel<<<1, 32, 0, p->stream>>>(d, p->d_lagrange);
-        TRY_P(cudaGetLastError());
+        p->h_lagrange = lagrange_block(d);
+        TRY_P(cudaMemcpyAsync(p->d_lagrange, p->h_lagrange.data(), (size_t)2 * (d + 1) * 32, cudaMemcpyHostToDevice, p->stream));
     }
     const size_t hRes = up((size_t)(d + 1) * 64 + 64), hTail = up((size_t)nv * (d + 2) * 32), hSt = up(2 * sizeof(b2::State));
     const size_t hEager = up((size_t)EAGER_CHUNKS * EAGER_SLOT_WORDS * 4);
@@ -646,9 +717,10 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
         // round 1 was summed in EAGER_CHUNKS pieces behind the upload: wait for the last piece, add the pieces, finish
         p->eager_valid = false;
         volatile uint32_t* flag = p->h_eager + (size_t)(EAGER_CHUNKS - 1) * EAGER_SLOT_WORDS + sck::MAX_NPTS * 8;
-        unsigned long long spins = 0;
+        SpinWait sw;
         while (*flag != p->eager_epoch) {
-            if ((++spins & 0xfffff) == 0) {
+            sw.pause();
+            if (sw.check_now()) {
                 cudaError_t q = cudaStreamQuery(p->stream);
                 if (q != cudaSuccess && q != cudaErrorNotReady) return fail(SC_ERR_CUDA, "round-1 chunk kernel failed: %s", cudaGetErrorString(q));
                 if (q == cudaSuccess && *flag != p->eager_epoch) return fail(SC_ERR_CUDA, "round-1 chunks finished without publishing");
@@ -689,9 +761,10 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
         sc_prover* w = (p->comm && p->wait_on) ? p->wait_on : p;
         volatile uint32_t* flag = w->h_result + (size_t)(p->d + 1) * 16;
         const uint32_t want = w->seq;
-        unsigned long long spins = 0;
+        SpinWait sw;
         while (*flag != want) {
-            if ((++spins & 0xfffff) == 0) {  // every ~1M polls make sure the kernel has not died
+            sw.pause();
+            if (sw.check_now()) {  // every 64K polls make sure the kernel has not died
                 cudaError_t q = cudaStreamQuery(p->stream);
                 if (q != cudaSuccess && q != cudaErrorNotReady) return fail(SC_ERR_CUDA, "round kernel failed: %s", cudaGetErrorString(q));
                 if (q == cudaSuccess && *flag != want) return fail(SC_ERR_CUDA, "round finished without publishing its result");
@@ -860,6 +933,7 @@ void sc_prover_destroy(sc_prover* p) {
     if (p->sub) { p->sub->stream = p->sub->own_stream; sc_prover_destroy(p->sub); cudaSetDevice(p->device); }
     cudaFree(p->d_gather); cudaFree(p->d_evals_g); cudaFree(p->d_canon_g); cudaFree(p->d_sub_tabs);
     if (p->owns_tab0) device_free(p->slab0, p->slab0_bytes, p->device);
+    device_free(p->adopted, p->adopted_bytes, p->device);
     device_free(p->slabA, p->slabA_bytes, p->device);  // one slab: ping-pong tables and every small device array
     host_mapped_free(p->h_result, p->h_result_bytes, p->device);  // one pinned block: results, tail read-back, transcript state
     for (auto e : p->ev) if (e) cudaEventDestroy(e);
@@ -869,17 +943,24 @@ void sc_prover_destroy(sc_prover* p) {
     delete p;
 }
 
+#define NEED_HANDLE(p) \
+    if (!(p)) return fail(SC_ERR_BAD_INPUT, "null prover handle")
+
 int sc_prover_reset(sc_prover* p) {
+    NEED_HANDLE(p);
     p->round = 0;
     p->cur = 0;
     p->randomness.clear();
     p->launches = 0;
     p->tc_rounds = 0;
     p->eager_valid = false;  // a pre-computed first round belongs to the proof that follows its upload only
+    if (p->comm) comm_clear_error(p);  // a timed-out exchange invalidated the previous proof, not the communicator
     return SC_OK;
 }
 
 int sc_prover_load_tables(sc_prover* p, const uint64_t* const* tables) {
+    NEED_HANDLE(p);
+    if (!tables) return fail(SC_ERR_BAD_INPUT, "null table list");
     if (!p->owns_tab0) return fail(SC_ERR_BAD_INPUT, "handle was created over caller-owned device tables");
     CUDA_TRY(cudaSetDevice(p->device));
     // Pipelined path: round 1 needs no challenge, so it is summed chunk by chunk behind the copies (the upload of 1.5 GiB
@@ -941,6 +1022,7 @@ int sc_prover_load_tables(sc_prover* p, const uint64_t* const* tables) {
 }
 
 int sc_prover_set_stream(sc_prover* p, void* cuda_stream) {
+    NEED_HANDLE(p);
     CUDA_TRY(cudaSetDevice(p->device));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     p->stream = cuda_stream ? (cudaStream_t)cuda_stream : p->own_stream;
@@ -948,16 +1030,19 @@ int sc_prover_set_stream(sc_prover* p, void* cuda_stream) {
 }
 
 int sc_prove_round(sc_prover* p, const uint64_t* r_or_null, uint64_t* evals_out) {
+    NEED_HANDLE(p);
+    if (!evals_out) return fail(SC_ERR_BAD_INPUT, "null output buffer");
     int rc = prove_round_impl(p, r_or_null, true);
     if (rc) return rc;
     memcpy(evals_out, p->h_evals, (size_t)(p->d + 1) * 32);
     return SC_OK;
 }
 
-uint32_t sc_prover_max_multiplicands(const sc_prover* p) { return p->d; }
-uint32_t sc_prover_num_vars(const sc_prover* p) { return p->nv; }
-uint32_t sc_prover_round(const sc_prover* p) { return p->round; }
+uint32_t sc_prover_max_multiplicands(const sc_prover* p) { return p ? p->d : 0; }
+uint32_t sc_prover_num_vars(const sc_prover* p) { return p ? p->nv : 0; }
+uint32_t sc_prover_round(const sc_prover* p) { return p ? p->round : 0; }
 uint32_t sc_prover_randomness(const sc_prover* p, uint64_t* out, uint32_t cap) {
+    if (!p) return 0;
     uint32_t n = (uint32_t)(p->randomness.size() / 4);
     uint32_t c = n < cap ? n : cap;
     if (out && c) memcpy(out, p->randomness.data(), (size_t)c * 32);
@@ -965,11 +1050,14 @@ uint32_t sc_prover_randomness(const sc_prover* p, uint64_t* out, uint32_t cap) {
 }
 
 int sc_prover_push_randomness(sc_prover* p, const uint64_t r[4]) {
+    NEED_HANDLE(p);
+    if (!r) return fail(SC_ERR_BAD_INPUT, "null challenge");
     p->randomness.insert(p->randomness.end(), r, r + 4);
     return SC_OK;
 }
 
 int sc_prover_table(const sc_prover* p, uint32_t j, uint64_t* out, uint64_t cap_elems, uint64_t* len_out) {
+    NEED_HANDLE(p);
     if (j >= p->T) return fail(SC_ERR_BAD_INPUT, "table %u out of range", j);
     // after round i >= 2 the tables have been folded i-1 times
     if (p->comm && p->round >= p->switch_round) {  // replicated rounds: the full (small) tables live on the sub-prover
@@ -1010,6 +1098,8 @@ int sc_prover_table(const sc_prover* p, uint32_t j, uint64_t* out, uint64_t cap_
 }
 
 int sc_ml_prove(sc_prover* p, sc_blake2b512_rng* rng, uint64_t* evals_out, uint64_t* randomness_out) {
+    NEED_HANDLE(p);
+    if (!rng || !evals_out) return fail(SC_ERR_BAD_INPUT, "null rng or output buffer");
     if (p->round != 0) return fail(SC_ERR_BAD_INPUT, "sc_ml_prove needs a prover at round 0 (got %u)", p->round);
     b2::State* st = (b2::State*)rng;
     uint8_t info[16];
@@ -1068,12 +1158,13 @@ void sc_synth_table_at(uint64_t* out, uint64_t first_elem, uint64_t n_elems, uin
 }
 
 uint32_t sc_prover_round_times_ms(const sc_prover* p, float* out, uint32_t cap) {
+    if (!p) return 0;
     uint32_t c = p->nv < cap ? p->nv : cap;
     if (out && c) memcpy(out, p->round_ms.data(), c * sizeof(float));
     return p->nv;
 }
-uint64_t sc_prover_launch_count(const sc_prover* p) { return p->launches; }
-uint64_t sc_prover_tc_round_count(const sc_prover* p) { return p->tc_rounds; }
+uint64_t sc_prover_launch_count(const sc_prover* p) { return p ? p->launches : 0; }
+uint64_t sc_prover_tc_round_count(const sc_prover* p) { return p ? p->tc_rounds : 0; }
 
 void sc_release_cached_memory(void) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -1102,6 +1193,7 @@ int sc_fr_interpolate(const uint64_t* evals, uint32_t n_evals, const uint64_t r[
     return SC_OK;
 }
 int sc_prover_set_timing(sc_prover* p, int enabled) {
+    NEED_HANDLE(p);
     p->want_timing = enabled != 0;
     if (p->want_timing) {
         CUDA_TRY(cudaSetDevice(p->device));
