@@ -138,6 +138,11 @@ SC_API uint64_t sc_prover_launch_count(const sc_prover *p);
  * least SC_TC_MIN_PAIRS output pairs, default 2^14).  Environment: SC_NO_TC=1 keeps every round on the plain kernels,
  * SC_TC_MIN_PAIRS=<n> moves the threshold (tests use 128 to cover the path at small sizes). */
 SC_API uint64_t sc_prover_tc_round_count(const sc_prover *p);
+/* ... and how many rounds were served by the resident kernel: sc_ml_prove / sc_gkr_prove run every round with at most
+ * SC_RES_MAX_PAIRS output pairs (default 2^16) inside ONE cooperative launch that stays on the GPU and exchanges the fold
+ * constants / raw sums with the host transcript through mapped memory (no launch per round).  SC_NO_RESIDENT=1 disables it;
+ * sc_prove_round (caller-driven rounds) never uses it. */
+SC_API uint64_t sc_prover_resident_round_count(const sc_prover *p);
 
 /* Handles return their device slab (<= 256 MiB), pinned result block and stream to a small per-device cache that later
  * handles reuse (allocation latency dominates small proofs such as the two phases of a GKR round).  This frees it;

@@ -272,6 +272,10 @@ class ProverState:
     def launch_count(self):
         return int(capi.lib().sc_prover_launch_count(self._h))
 
+    def resident_round_count(self):
+        """Rounds served by the resident kernel (one cooperative launch for all small rounds) since creation/reset."""
+        return int(capi.lib().sc_prover_resident_round_count(self._h))
+
     def tc_round_count(self):
         """Fold rounds that ran on the TMA + tensor-core kernel since creation/reset."""
         return int(capi.lib().sc_prover_tc_round_count(self._h))

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <sched.h>
+#include <time.h>
 
 #include <cstdarg>
 #include <cstdio>
@@ -75,6 +76,7 @@ struct SpinWait {
 struct DeviceInfo {
     bool ready = false;
     int sms = 0;
+    int khz = 0;  // SM clock: cudaDeviceGetAttribute(cudaDevAttrClockRate) takes 1-4 ms per call (measured), so it is read once
 };
 DeviceInfo g_dev[64];
 std::mutex g_dev_mu;  // one-time per-device initialisation (constants, attributes); handles may live on different threads
@@ -94,6 +96,7 @@ int ensure_device(int device) {
         CUDA_TRY(fr::fr_init_constants());
         CUDA_TRY(sck::tail_init_constants());
         g_dev[device].sms = prop.multiProcessorCount;
+        cudaDeviceGetAttribute(&g_dev[device].khz, cudaDevAttrClockRate, device);
         g_dev[device].ready = true;
     }
     return SC_OK;
@@ -114,6 +117,10 @@ struct AllocCache {
 };
 AllocCache g_cache[64];
 std::mutex g_cache_mu;
+// resident rounds: host <-> device words (see resident_kernel.cuh); byte offsets inside the mapped block
+constexpr size_t RES_OFF_CONSTS = 0, RES_OFF_SUMS = 512, RES_OFF_ERROR = 1024, RES_OFF_ABORT = 1088, RES_HOST_BYTES = 1280;
+constexpr size_t RES_BCAST_BYTES = 64 * 8 + 64;
+constexpr unsigned long long RES_MAX_PAIRS_DEFAULT = 1ull << 16;
 constexpr uint32_t EAGER_CHUNKS = 8;
 constexpr uint32_t EAGER_SLOT_WORDS = sck::MAX_NPTS * 8 + 8;  // raw sums, then the flag word
 constexpr size_t CACHE_MAX_ENTRIES = 8;
@@ -261,7 +268,7 @@ struct sc_prover {
     bool direct_results = true;  // rounds deliver their message through mapped host memory + flag
     bool direct_active = false;  // ... and the round just issued did so
     bool exchange = false;       // sharded round: fuse the partial-sum exchange into the round kernel
-    uint64_t launches = 0, tc_rounds = 0;
+    uint64_t launches = 0, tc_rounds = 0, res_rounds = 0;
     // where the d+1 results of the last round live on the device (local buffers, the summed copies, or the sub-prover's)
     uint32_t *out_evals = nullptr, *out_canon = nullptr;
     // ---- multi-GPU (capi_multi.inc): nv is GLOBAL, nv_local = nv - log2(ranks) is what this rank's shard spans
@@ -279,6 +286,16 @@ struct sc_prover {
     uint8_t* d_scaled = nullptr;
     std::vector<uint32_t> h_offsets, h_indices;
     std::vector<uint64_t> h_lagrange;  // staging copy of d_lagrange (uploaded asynchronously)
+    // Resident rounds (resident_kernel.cuh): set by run_rounds for the proof in flight
+    uint32_t res_first = 0;            // first (1-based) round served by the resident kernel; 0 = none
+    bool res_running = false;          // the kernel is on the GPU, waiting for fold constants
+    uint32_t res_seq0 = 0;             // sequence number of its first round
+    unsigned long long res_max_pairs = 0;
+    uint32_t *h_res = nullptr, *d_res = nullptr;  // mapped block: [64 x {limb,seq}] constants | [40 x {limb,seq}] sums | error | abort
+    uint32_t* d_res_bcast = nullptr;   // device: [64 x {limb,seq}] + abort word
+    unsigned int* d_res_counters = nullptr;
+    long long* d_res_prof = nullptr;   // SC_RES_PROF=1: per-round cycle counts of CTA 0
+    double res_host_us[64][3] = {};    // ... and host-side microseconds per resident round: constants out, wait, finish
     void* adopted = nullptr;           // a device block whose ownership was handed to this handle (freed on destroy)
     size_t adopted_bytes = 0;
 };
@@ -546,6 +563,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     const size_t oTe = take((size_t)nv * (d + 1) * 32), oTc = take((size_t)nv * 32), oSt = take(2 * sizeof(b2::State));
     const size_t oMaps = take((size_t)4 * T * sizeof(CUtensorMap));
     const size_t oScaled = take(n_products);
+    const size_t oResB = take(RES_BCAST_BYTES), oResC = take(64 * sizeof(unsigned int));
     TRY_P(device_alloc((void**)&p->slabA, off, &p->slabA_bytes, device));
     uint8_t* base = (uint8_t*)p->slabA;
     for (uint32_t j = 0; j < T; j++) {
@@ -556,6 +574,8 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     p->d_offsets = (uint32_t*)(base + oOff); p->d_indices = (uint32_t*)(base + oIdx); p->d_first = base + oFirst;
     p->d_coeffs = (uint32_t*)(base + oCoef); p->d_partials = (uint32_t*)(base + oPart); p->d_counter = (unsigned int*)(base + oCnt);
     p->d_evals = (uint32_t*)(base + oEv); p->d_canon = (uint32_t*)(base + oCa);
+    p->d_res_bcast = (uint32_t*)(base + oResB); p->d_res_counters = (unsigned int*)(base + oResC);
+    TRY_P(cudaMemsetAsync(p->d_res_bcast, 0, RES_BCAST_BYTES, p->stream));  // a recycled slab may hold another handle's sequence numbers
     p->d_tail_evals = (uint32_t*)(base + oTe); p->d_tail_chal = (uint32_t*)(base + oTc); p->d_st = (b2::State*)(base + oSt);
     {
         // TMA descriptors (fold rounds with >= tc_min_pairs output pairs run on the TMA + tensor-core kernel)
@@ -631,7 +651,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     }
     const size_t hRes = up((size_t)(d + 1) * 64 + 64), hTail = up((size_t)nv * (d + 2) * 32), hSt = up(2 * sizeof(b2::State));
     const size_t hEager = up((size_t)EAGER_CHUNKS * EAGER_SLOT_WORDS * 4);
-    TRY_P(host_mapped_alloc((void**)&p->h_result, hRes + hTail + hSt + hEager, &p->h_result_bytes, device));
+    TRY_P(host_mapped_alloc((void**)&p->h_result, hRes + hTail + hSt + hEager + RES_HOST_BYTES, &p->h_result_bytes, device));
     memset(p->h_result, 0, hRes);
     TRY_P(cudaHostGetDevicePointer((void**)&p->d_result, p->h_result, 0));
     p->h_evals = p->h_result;
@@ -641,6 +661,13 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     p->h_eager = (uint32_t*)((uint8_t*)p->h_result + hRes + hTail + hSt);
     p->d_eager = (uint32_t*)((uint8_t*)p->d_result + hRes + hTail + hSt);
     memset(p->h_eager, 0, hEager);
+    p->h_res = (uint32_t*)((uint8_t*)p->h_result + hRes + hTail + hSt + hEager);
+    p->d_res = (uint32_t*)((uint8_t*)p->d_result + hRes + hTail + hSt + hEager);
+    memset(p->h_res, 0, RES_HOST_BYTES);  // recycled pinned blocks hold another handle's sequence numbers
+    {
+        const char* env = getenv("SC_RES_MAX_PAIRS");
+        p->res_max_pairs = getenv("SC_NO_RESIDENT") ? 0 : (env ? strtoull(env, nullptr, 10) : RES_MAX_PAIRS_DEFAULT);
+    }
     p->host_post = !getenv("SC_TAIL") && !getenv("SC_NO_HOST_POST");
     p->h_prev.assign((size_t)(d + 1) * 4, 0);
     p->ev.assign(2 * (size_t)nv, nullptr);  // CUDA events are created on demand (sc_prover_set_timing)
@@ -698,6 +725,146 @@ void host_finish_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
     }
 }
 
+// ---- resident rounds (resident_kernel.cuh) ---------------------------------------------------------------------------
+// First (1-based) round the resident kernel serves for a whole-proof call (run_rounds), or 0.
+uint32_t resident_first_round(const sc_prover* p) {
+    if (p->res_max_pairs == 0 || p->comm || !p->host_post || !p->direct_results || p->d < 1 || p->d > (uint32_t)sck::MAX_NPTS || !p->d_lagrange || getenv("SC_TAIL"))
+        return 0;
+    for (uint32_t i = 2; i <= p->nv_local; i++)
+        if (((unsigned long long)1 << (p->nv_local - i)) <= p->res_max_pairs) return i;
+    return 0;
+}
+
+// Enqueue the resident kernel behind the launch of round res_first - 1 (p->cur already names the buffer that round writes).
+int resident_launch(sc_prover* p) {
+    const uint32_t first = p->res_first, nv = p->nv_local, d = p->d;
+    sck::ResidentParams q;
+    memset(&q, 0, sizeof(q));
+    sck::RoundParams& rp = q.rp;
+    rp.prod_offsets = p->d_offsets; rp.prod_indices = p->d_indices; rp.prod_first = p->d_first; rp.coeffs = p->d_coeffs;
+    rp.prod_scaled = p->d_scaled;
+    rp.n_products = p->n_products; rp.n_tables = p->T; rp.defer_coeff = (p->n_products == 1) ? 1u : 0u;
+    rp.t0 = 0; rp.write_fold = 1; rp.skip1 = 1; rp.degree = d;
+    q.ptrs[0] = p->d_ptr0; q.ptrs[1] = p->d_ptrA; q.ptrs[2] = p->d_ptrB;
+    q.cur = p->cur;
+    q.n_rounds = nv - first + 1;
+    q.n_pairs_first = (unsigned long long)1 << (nv - first);
+    q.seq0 = p->seq + 1;
+    q.h_consts = (const uint32_t*)((uint8_t*)p->d_res + RES_OFF_CONSTS);
+    q.h_sums = (uint32_t*)((uint8_t*)p->d_res + RES_OFF_SUMS);
+    q.h_error = (uint32_t*)((uint8_t*)p->d_res + RES_OFF_ERROR);
+    q.h_abort = (const uint32_t*)((uint8_t*)p->d_res + RES_OFF_ABORT);
+    q.d_bcast = p->d_res_bcast;
+    q.d_abort = p->d_res_bcast + 128;
+    q.partials = p->d_partials;
+    q.counters = p->d_res_counters;
+    const int khz = g_dev[p->device].khz;
+    static const double secs = getenv("SC_RES_TIMEOUT_S") ? atof(getenv("SC_RES_TIMEOUT_S")) : 10.0;
+    q.timeout = (long long)(secs * (khz > 0 ? khz : 1965000) * 1000.0);
+    *(volatile uint32_t*)((uint8_t*)p->h_res + RES_OFF_ERROR) = 0;
+    if (const char* f = getenv("SC_RES_FLAGS")) q.flags = (uint32_t)atoi(f);
+    if (getenv("SC_RES_PROF")) {
+        if (!p->d_res_prof) CUDA_TRY(cudaMalloc(&p->d_res_prof, 64 * 4 * sizeof(long long)));
+        CUDA_TRY(cudaMemsetAsync(p->d_res_prof, 0, 64 * 4 * sizeof(long long), p->stream));
+        q.prof = p->d_res_prof;
+    }
+    CUDA_TRY(cudaMemsetAsync(p->d_res_counters, 0, 64 * sizeof(unsigned int), p->stream));
+    unsigned long long need = (q.n_pairs_first + sck::RES_THREADS - 1) / sck::RES_THREADS;
+    unsigned long long cap = (unsigned long long)sck::resident_max_grid(d, p->device, g_dev[p->device].sms);
+    if (cap * 2 > (unsigned long long)p->max_grid) cap = p->max_grid / 2;  // partials: [2][grid][NPTS][8]
+    const int grid = (int)(need < cap ? (need ? need : 1) : cap);
+    cudaError_t e = sck::launch_resident(d, grid, q, p->stream);
+    if (e != cudaSuccess) return fail(SC_ERR_CUDA, "resident kernel launch: %s", cudaGetErrorString(e));
+    p->launches++;
+    p->res_running = true;
+    p->res_seq0 = q.seq0;
+    return SC_OK;
+}
+
+// The host abandons a proof whose resident kernel is still waiting: tell it to leave (it would otherwise time out).
+void resident_abort(sc_prover* p) {
+    if (!p->res_running) return;
+    *(volatile uint32_t*)((uint8_t*)p->h_res + RES_OFF_ABORT) = p->res_seq0;
+    __sync_synchronize();
+    cudaStreamSynchronize(p->stream);
+    p->res_running = false;
+}
+
+// One round served by the resident kernel: prove_round's state machine, then fold constants out / raw sums in.
+int resident_round(sc_prover* p, const uint64_t* r) {
+    p->randomness.insert(p->randomness.end(), r, r + 4);  // prover.rs:82
+    p->round += 1;
+    if (p->round > p->nv) return fail(SC_ERR_PANIC_NOT_ACTIVE, "Prover is not active");
+    const uint32_t seq = ++p->seq, d = p->d;
+    const bool prof = p->d_res_prof != nullptr;
+    auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    const double h0 = prof ? now_us() : 0;
+    // C[k] = r * 2^(32k+64) mod p as plain integers (fr.cuh fold_const): Montgomery-multiply r by the raw 2^(32k+64) mod p
+    static const hfr::F X7 = {{0x355094eacaaf6b13ULL, 0xf6b10cb369a568efULL, 0xe2c926a640cc3869ULL, 0x736a6d3bed269aadULL}};  // 2^288 mod p
+    hfr::F rr;
+    memcpy(&rr, r, 32);
+    uint64_t* hc = (uint64_t*)((uint8_t*)p->h_res + RES_OFF_CONSTS);
+    for (int k = 0; k < 8; k++) {
+        hfr::F x = {{0, 0, 0, 0}};
+        if (k < 6) x.l[(k + 2) / 2] = (uint64_t)1 << (32 * ((k + 2) & 1));
+        else if (k == 6) x = hfr::ONE;
+        else x = X7;
+        const hfr::F c = hfr::mul(rr, x);
+        for (int i = 0; i < 4; i++) {
+            __atomic_store_n(hc + k * 8 + 2 * i, (uint64_t)(uint32_t)c.l[i] | ((uint64_t)seq << 32), __ATOMIC_RELAXED);
+            __atomic_store_n(hc + k * 8 + 2 * i + 1, (uint64_t)(c.l[i] >> 32) | ((uint64_t)seq << 32), __ATOMIC_RELAXED);
+        }
+    }
+    const double h1 = prof ? now_us() : 0;
+    // wait for the d raw sums: every limb arrives as one {limb, seq} word
+    const uint64_t* hs = (const uint64_t*)((uint8_t*)p->h_res + RES_OFF_SUMS);
+    const uint32_t n_words = d * 8;
+    SpinWait sw;
+    for (uint32_t w = 0; w < n_words; w++) {
+        uint64_t v;
+        while (((v = __atomic_load_n(hs + w, __ATOMIC_RELAXED)) >> 32) != seq) {
+            sw.pause();
+            if (sw.check_now()) {
+                if (*(volatile uint32_t*)((uint8_t*)p->h_res + RES_OFF_ERROR)) {
+                    p->res_running = false;
+                    return fail(p->comm ? SC_ERR_COMM : SC_ERR_CUDA, "resident kernel gave up waiting (host constants or a peer GPU did not arrive in time)");
+                }
+                cudaError_t q = cudaStreamQuery(p->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) { p->res_running = false; return fail(SC_ERR_CUDA, "resident kernel failed: %s", cudaGetErrorString(q)); }
+                if (q == cudaSuccess && (__atomic_load_n(hs + w, __ATOMIC_RELAXED) >> 32) != seq) {
+                    p->res_running = false;
+                    return fail(SC_ERR_CUDA, "resident kernel ended without publishing round %u", p->round);
+                }
+            }
+        }
+        p->h_result[w] = (uint32_t)v;
+    }
+    __sync_synchronize();
+    const double h2 = prof ? now_us() : 0;
+    p->raw_npts = d;
+    p->used_skip1 = true;
+    host_finish_round(p, p, r);
+    memcpy(p->h_prev.data(), p->h_evals, (size_t)(d + 1) * 32);
+    p->cur = (p->cur == 1) ? 2 : 1;
+    if (prof) {
+        double* h = p->res_host_us[(p->round - p->res_first) & 63];
+        h[0] = h1 - h0; h[1] = h2 - h1; h[2] = now_us() - h2;
+        if (p->round == p->nv) {
+            cudaStreamSynchronize(p->stream);
+            long long hp[64 * 4];
+            cudaMemcpy(hp, p->d_res_prof, sizeof(hp), cudaMemcpyDeviceToHost);
+            for (uint32_t k = 0; k + p->res_first <= p->nv && k < 64; k++)
+                fprintf(stderr, "resident round %u: device wait %lld accumulate %lld reduce %lld publish %lld cycles | host consts %.2f wait %.2f finish %.2f us\n",
+                        p->res_first + k, hp[k * 4], hp[k * 4 + 1], hp[k * 4 + 2], hp[k * 4 + 3], p->res_host_us[k][0], p->res_host_us[k][1], p->res_host_us[k][2]);
+        }
+    }
+    p->res_rounds++;
+    if (p->round == p->nv) p->res_running = false;  // the kernel has published its last round and leaves by itself
+    p->out_evals = nullptr;  // the message of a resident round lives on the host only
+    p->out_canon = nullptr;
+    return SC_OK;
+}
+
 // prove_round state machine (prover.rs:78-98) + device round + D2H of the d+1 results into the pinned buffers.
 int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
     if (r_or_null) {
@@ -745,6 +912,7 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
         p->out_canon = p->d_canon;
         p->direct_active = true;
         if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));  // the round's work ran during the upload
+        if (p->res_first && p->round + 1 == p->res_first) return resident_launch(p);
         return SC_OK;
     }
     if (p->comm) {
@@ -756,6 +924,20 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
     }
     if (rc) return rc;
     if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));
+    if (p->res_first && p->round + 1 == p->res_first) {
+        // the next round is the first resident one: queue the kernel now, so that it is already polling when this
+        // round's challenge has been drawn
+        if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * p->round], p->stream));
+        rc = resident_launch(p);
+        if (rc) return rc;
+        if (timed) {  // one interval for the whole resident launch; the later rounds have no launch of their own
+            CUDA_TRY(cudaEventRecord(p->ev[2 * p->round + 1], p->stream));
+            for (uint32_t i = p->round + 1; i < p->nv; i++) {
+                CUDA_TRY(cudaEventRecord(p->ev[2 * i], p->stream));
+                CUDA_TRY(cudaEventRecord(p->ev[2 * i + 1], p->stream));
+            }
+        }
+    }
     if (p->direct_active) {
         // the last block wrote the message into mapped pinned memory and then the flag: spin instead of copy + sync
         sc_prover* w = (p->comm && p->wait_on) ? p->wait_on : p;
@@ -873,14 +1055,21 @@ int run_rounds(sc_prover* p, b2::State* st, uint64_t* evals_out, uint64_t* chall
     bool have_r = false;
     const uint32_t tail_first = tail_first_round(p);
     p->timing = true;
+    p->res_first = resident_first_round(p);
+    auto bail = [&](int rc) {
+        p->timing = false;
+        resident_abort(p);
+        p->res_first = 0;
+        return rc;
+    };
     for (uint32_t i = 0; i < nv; i++) {
         if (i + 1 == tail_first && have_r && st->buflen % 8 == 0) {
             int rc = run_tail(p, st, tail_first, r, evals_out, challenges_out);
-            if (rc) { p->timing = false; return rc; }
+            if (rc) return bail(rc);
             break;
         }
-        int rc = prove_round_impl(p, have_r ? r : nullptr, true);
-        if (rc) { p->timing = false; return rc; }
+        int rc = (p->res_first && i + 1 >= p->res_first) ? resident_round(p, r) : prove_round_impl(p, have_r ? r : nullptr, true);
+        if (rc) return bail(rc);
         memcpy(evals_out + (size_t)i * (d + 1) * 4, p->h_evals, (size_t)(d + 1) * 32);
         memcpy(msg.data() + 8, p->h_canon, (size_t)(d + 1) * 32);
         b2::update(st, msg.data(), msg.size());
@@ -888,6 +1077,7 @@ int run_rounds(sc_prover* p, b2::State* st, uint64_t* evals_out, uint64_t* chall
         have_r = true;
         memcpy(challenges_out + (size_t)i * 4, r, 32);
     }
+    p->res_first = 0;
     p->timing = false;
     if (p->want_timing) {
         cudaStreamSynchronize(p->stream);
@@ -929,10 +1119,12 @@ int sc_prover_create_device(sc_prover** out, uint32_t nv, uint32_t n_tables, con
 void sc_prover_destroy(sc_prover* p) {
     if (!p) return;
     cudaSetDevice(p->device);
+    resident_abort(p);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->sub) { p->sub->stream = p->sub->own_stream; sc_prover_destroy(p->sub); cudaSetDevice(p->device); }
     cudaFree(p->d_gather); cudaFree(p->d_evals_g); cudaFree(p->d_canon_g); cudaFree(p->d_sub_tabs);
     if (p->owns_tab0) device_free(p->slab0, p->slab0_bytes, p->device);
+    cudaFree(p->d_res_prof);
     device_free(p->adopted, p->adopted_bytes, p->device);
     device_free(p->slabA, p->slabA_bytes, p->device);  // one slab: ping-pong tables and every small device array
     host_mapped_free(p->h_result, p->h_result_bytes, p->device);  // one pinned block: results, tail read-back, transcript state
@@ -953,6 +1145,7 @@ int sc_prover_reset(sc_prover* p) {
     p->randomness.clear();
     p->launches = 0;
     p->tc_rounds = 0;
+    p->res_rounds = 0;
     p->eager_valid = false;  // a pre-computed first round belongs to the proof that follows its upload only
     if (p->comm) comm_clear_error(p);  // a timed-out exchange invalidated the previous proof, not the communicator
     return SC_OK;
@@ -1165,6 +1358,7 @@ uint32_t sc_prover_round_times_ms(const sc_prover* p, float* out, uint32_t cap) 
 }
 uint64_t sc_prover_launch_count(const sc_prover* p) { return p ? p->launches : 0; }
 uint64_t sc_prover_tc_round_count(const sc_prover* p) { return p ? p->tc_rounds : 0; }
+uint64_t sc_prover_resident_round_count(const sc_prover* p) { return p ? p->res_rounds : 0; }
 
 void sc_release_cached_memory(void) {
     std::lock_guard<std::mutex> lk(g_cache_mu);

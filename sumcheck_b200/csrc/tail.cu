@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "resident_kernel.cuh"
 #include "tail_kernel.cuh"
 #include "tc_round.cuh"
 
@@ -111,6 +112,49 @@ cudaError_t launch_fold_round_tc(uint32_t npts, int sms, int max_grid, const Rou
         default: round_tc_kernel<5><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp); break;
     }
     return cudaGetLastError();
+}
+
+// ---- resident rounds (resident_kernel.cuh): cooperative launch, so that every CTA is co-resident by construction
+template <int NPTS>
+static int resident_blocks_per_sm() {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, resident_kernel<NPTS>, RES_THREADS, 0);
+    return nb < 1 ? 1 : (nb > 2 ? 2 : nb);
+}
+int resident_max_grid(uint32_t npts, int device, int sms) {
+    static int cached[64][MAX_NPTS + 1] = {};
+    int& v = cached[device & 63][npts <= (uint32_t)MAX_NPTS ? npts : 0];
+    if (!v) {
+        switch (npts) {
+            case 1: v = resident_blocks_per_sm<1>(); break;
+            case 2: v = resident_blocks_per_sm<2>(); break;
+            case 3: v = resident_blocks_per_sm<3>(); break;
+            case 4: v = resident_blocks_per_sm<4>(); break;
+            default: v = resident_blocks_per_sm<5>(); break;
+        }
+    }
+    return v * sms;
+}
+
+cudaError_t launch_resident(uint32_t npts, int grid, const ResidentParams& rp, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(RES_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = getenv("SC_RES_NO_COOP") ? 0 : 1;  // measured: no difference in launch cost; cooperative guarantees co-residency
+    switch (npts) {
+        case 1: return cudaLaunchKernelEx(&cfg, resident_kernel<1>, rp);
+        case 2: return cudaLaunchKernelEx(&cfg, resident_kernel<2>, rp);
+        case 3: return cudaLaunchKernelEx(&cfg, resident_kernel<3>, rp);
+        case 4: return cudaLaunchKernelEx(&cfg, resident_kernel<4>, rp);
+        case 5: return cudaLaunchKernelEx(&cfg, resident_kernel<5>, rp);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_tail(uint32_t degree, const TailParams& tp, cudaStream_t stream) {

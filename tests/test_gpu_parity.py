@@ -203,6 +203,73 @@ def test_prove_verify_evaluate_on_device(orc, nv, n_products, mult_range, shared
     assert e.value.code == -6
 
 
+# ------------------------------------------------------------------------------------------- resident rounds
+@pytest.mark.parametrize("nv,n_products,mult_range,shared,max_pairs", [
+    (2, 1, (2, 3), False, None),      # one resident round (round 2, a single pair)
+    (9, 1, (3, 4), False, None),      # every fold round resident: 2 CTAs -> 1 CTA
+    (13, 1, (3, 4), False, None),     # 32 CTAs at the start, the grid shrinks round by round
+    (15, 1, (2, 3), False, None),     # 128 CTAs, one pair per thread
+    (17, 1, (3, 4), False, 1 << 16),  # round 2 (2^15 pairs) and round 1 on the launch-per-round kernels, then resident with 2^15... pairs
+    (17, 1, (3, 4), False, 1 << 20),  # all fold rounds resident: several pairs per thread (grid-stride loop)
+    (12, 5, (1, 6), True, None),      # shared tables, repeats, short products
+    (12, 3, (2, 5), False, 128),      # hand-over in the middle: rounds up to 256 pairs by launches, then one resident CTA
+    (11, 1, (5, 6), False, None),     # d = 5: five summed points
+    (11, 2, (6, 8), False, None),     # d + 1 > 6: no claim shortcut -> no resident rounds (must still agree)
+])
+def test_resident_rounds(orc, monkeypatch, nv, n_products, mult_range, shared, max_pairs):
+    """Rounds served by the resident kernel (csrc/resident_kernel.cuh: ONE cooperative launch for all small rounds, fold
+    constants / raw sums exchanged with the host transcript through mapped memory) against the oracle, the launch-per-round
+    path (SC_NO_RESIDENT=1), the folded tables left in ProverState, a second proof on the same handle, and the counters."""
+    if max_pairs is not None:
+        monkeypatch.setenv("SC_RES_MAX_PAIRS", str(max_pairs))
+    tables, products = random_instance(9100 + 17 * nv + n_products, nv, n_products, mult_range, shared)
+    poly, opoly = both_polys(orc, nv, tables, products)
+    got, rand = assert_same_proof(orc, poly, opoly)   # proof bytes, randomness, final 2-entry tables
+    import ctypes as C
+    st = sc.IPForMLSumcheck.prover_init(poly)
+    ev = np.zeros((nv, poly.max_multiplicands + 1, 4), dtype=np.uint64)
+    for rep in range(2):
+        rng = sc.Blake2b512Rng.setup()
+        ev[:] = 0
+        assert sc.lib().sc_ml_prove(st._h, C.byref(rng.state), ev.ctypes.data_as(sc.capi.U64P), None) == 0
+        assert np.array_equal(ev, got)
+        lim = max_pairs if max_pairs is not None else 1 << 16
+        want = sum(1 for i in range(2, nv + 1) if (1 << (nv - i)) <= lim) if poly.max_multiplicands <= 5 else 0
+        assert st.resident_round_count() == want
+        st.reset()
+    monkeypatch.setenv("SC_NO_RESIDENT", "1")
+    st2 = sc.IPForMLSumcheck.prover_init(poly)
+    rng = sc.Blake2b512Rng.setup()
+    ev2 = np.zeros_like(ev)
+    assert sc.lib().sc_ml_prove(st2._h, C.byref(rng.state), ev2.ctypes.data_as(sc.capi.U64P), None) == 0
+    assert st2.resident_round_count() == 0
+    assert np.array_equal(ev2, got)
+
+
+def test_resident_rounds_special_values(orc):
+    """0 / 1 / p-1 tables and a zero coefficient through the resident rounds."""
+    nv = 10
+    rnd = random.Random(12)
+    pool = [0, 1, pm.P - 1, 2, pm.P - 2, (1 << 248) - 1, pm.P >> 1]
+    tables = [[rnd.choice(pool) for _ in range(1 << nv)] for _ in range(3)]
+    products = [(pm.P - 1, [0, 1, 2]), (1, [2, 2]), (0, [1])]
+    poly, opoly = both_polys(orc, nv, tables, products)
+    assert_same_proof(orc, poly, opoly)
+
+
+def test_resident_abandoned_proof_does_not_hang(orc):
+    """A handle destroyed / reset while nothing is in flight, and many handles in a row (recycled pinned blocks carry other
+    handles' sequence numbers — they are cleared at creation): proofs stay correct."""
+    nv = 8
+    for k in range(6):
+        tabs = [orc.synth_table(1 << nv, 300 + 10 * k + j) for j in range(2)]
+        prods = [(orc.synth_table(1, 399 + k)[0], [0, 1])]
+        poly = build_poly(nv, tabs, prods)
+        proof = sc.MLSumcheck.prove(poly)
+        want = orc.ml_prove(orc.Poly(nv, tabs, prods))[0]
+        assert np.array_equal(np.stack([m.evaluations for m in proof]), want)
+
+
 # ------------------------------------------------------------------------------------------- tensor-core fold rounds
 @pytest.mark.parametrize("nv,n_products,mult_range,shared", [
     (9, 1, (3, 4), False),     # smallest shape with a 128-pair fold round (round 2 of nv=9): one tile, one CTA
@@ -218,6 +285,7 @@ def test_tensor_core_fold_rounds(orc, monkeypatch, nv, n_products, mult_range, s
     SC_TC_MIN_PAIRS so that small shapes cover one tile per CTA, several tiles per CTA and grid > tiles.  Same bytes as
     the oracle, the same folded tables, and identical to the plain kernels (SC_NO_TC=1)."""
     monkeypatch.setenv("SC_TC_MIN_PAIRS", "128")
+    monkeypatch.setenv("SC_RES_MAX_PAIRS", "64")   # the resident kernel would otherwise take every round of these small shapes
     tables, products = random_instance(7000 + 13 * nv + n_products, nv, n_products, mult_range, shared)
     poly, opoly = both_polys(orc, nv, tables, products)
     got, rand = assert_same_proof(orc, poly, opoly)
@@ -351,11 +419,12 @@ def test_pipelined_upload_first_round(orc):
         ev = np.zeros((nv, 4, 4), dtype=np.uint64)
         st.prove_into(sc.Blake2b512Rng.setup(), ev)
         assert np.array_equal(ev, want)
-        assert st.launch_count() == 8 + nv - 1          # 8 chunk launches of round 1, then one launch per round
+        per_round = sum(1 for i in range(2, nv + 1) if (1 << (nv - i)) > (1 << 16))   # fold rounds with a launch of their own
+        assert st.launch_count() == 8 + per_round + 1   # 8 chunk launches of round 1, the large fold rounds, ONE resident launch
     st.reset()
     ev2 = np.zeros_like(ev)
     st.prove_into(sc.Blake2b512Rng.setup(), ev2)
-    assert np.array_equal(ev2, want) and st.launch_count() == nv
+    assert np.array_equal(ev2, want) and st.launch_count() == 1 + per_round + 1
 
 
 # ------------------------------------------------------------------------------------------- BASELINE.json sizes
