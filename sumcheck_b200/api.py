@@ -334,6 +334,17 @@ class MLSumcheck:
         return proof
 
     @staticmethod
+    def prove_into(polynomial, evals, device=0, randomness=None):
+        """MLSumcheck::prove through the one-call C entry point (sc_ml_prove_oneshot: create + upload + prove + destroy)
+        into a preallocated [nv, d+1, 4] array — what the Rust wrapper's `prove(&poly)` binds."""
+        coeffs, offsets, indices = polynomial._csr()
+        T = len(polynomial.flattened_ml_extensions)
+        tabs = (C.c_void_p * max(T, 1))(*[t.ctypes.data for t in polynomial.flattened_ml_extensions])
+        _check(capi.lib().sc_ml_prove_oneshot(polynomial.num_variables, T, tabs, len(polynomial.products), _p64(coeffs), _p32(offsets),
+                                              _p32(indices), device, _p64(evals), _p64(randomness) if randomness is not None else None))
+        return evals
+
+    @staticmethod
     def prove_as_subprotocol(fs_rng, polynomial, device=0):  # mod.rs:50-70
         if isinstance(fs_rng, Blake2b512Rng):
             state = _create(polynomial, device)

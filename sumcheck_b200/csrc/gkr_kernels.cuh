@@ -149,6 +149,26 @@ __global__ void __launch_bounds__(128) to_canonical_kernel(const uint32_t* in, u
 }
 
 // ---- multi-GPU helpers (capi_multi.inc)
+// Switch to replicated rounds: dst[j][g * len + e] = src[g * n_tables + j][e] — every rank PULLS the current shard of every
+// table from every rank (its own included) over NVLink peer memory, one launch instead of an NCCL all-gather per proof.
+// The peers' stores were fenced at GPU scope before their last block reported the previous round (finish_round), and this
+// rank has seen that round's global sums, so the data is complete; the loads bypass L1 (a stale line of an earlier proof).
+// blockIdx.y = g * n_tables + j.
+__global__ void __launch_bounds__(128) gather_tables_kernel(const uint32_t* const* src, uint32_t n_tables, unsigned long long len,
+                                                           uint32_t* dst, unsigned long long dst_table_stride) {
+    const uint32_t g = blockIdx.y / n_tables, j = blockIdx.y % n_tables;
+    const uint32_t* from = src[blockIdx.y];
+    uint32_t* to = dst + (size_t)j * dst_table_stride * 8 + (size_t)g * len * 8;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < len; e += (unsigned long long)gridDim.x * blockDim.x) {
+        Fr v;
+        asm volatile("ld.relaxed.sys.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v.l[0]), "=r"(v.l[1]), "=r"(v.l[2]), "=r"(v.l[3]), "=r"(v.l[4]), "=r"(v.l[5]), "=r"(v.l[6]), "=r"(v.l[7])
+                     : "l"(from + e * 8)
+                     : "memory");
+        fr::store(to + e * 8, v);
+    }
+}
+
 // evals[t] = sum over ranks of gathered[g][t]  (+ canonical form for the transcript); npts <= 32, one warp.
 // fix1: the ranks summed only t = 0, 2, .., d (slot 1 is zero); P(1) = P_prev(r) - P(0) with P_prev = evals_out's old content.
 __global__ void sum_partials_kernel(const uint32_t* gathered, uint32_t n_ranks, uint32_t npts, uint32_t* evals_out, uint32_t* canon_out,

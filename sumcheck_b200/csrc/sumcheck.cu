@@ -24,6 +24,7 @@
 #include "tail_params.cuh"
 #include "tmap_host.h"
 #include "host_fr.h"
+#include "host_copy.h"
 #include "tma_round1.cuh"
 
 static_assert(sizeof(sc_blake2b512_rng) == sizeof(b2::State), "sc_blake2b512_rng must be layout-identical to b2::State");
@@ -219,6 +220,7 @@ struct sc_prover {
     uint32_t nv = 0, T = 0, n_products = 0, d = 0, round = 0;
     uint64_t N = 0;
     bool owns_tab0 = true;
+    bool is_shard = false;  // one rank's shard of a sharded polynomial (capi_multi.inc); set before the first upload
     std::vector<uint64_t> randomness;  // ProverState.randomness, 4 u64 each
     std::vector<uint32_t*> tab0, bufA, bufB;  // per-table device pointers
     uint32_t *slab0 = nullptr, *slabA = nullptr, *slabB = nullptr;
@@ -510,10 +512,11 @@ int validate_products(uint32_t n_tables, uint32_t n_products, const uint32_t* of
 }
 
 int prescale_tables(sc_prover* p);
+int upload_tables(sc_prover* p, const uint64_t* const* tables);
 
 int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* const* tables, bool tables_on_device,
                   uint32_t n_products, const uint64_t* coeffs, const uint32_t* offsets, const uint32_t* indices, int device,
-                  const uint8_t* inherit_scaled = nullptr) {
+                  const uint8_t* inherit_scaled = nullptr, bool shard = false) {
     if (!out) return fail(SC_ERR_BAD_INPUT, "null output handle");
     *out = nullptr;
     if (nv == 0) return fail(SC_ERR_PANIC_CONSTANT, "Attempt to prove a constant.");
@@ -525,6 +528,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     rc = ensure_device(device);
     if (rc) return rc;
     sc_prover* p = new sc_prover();
+    p->is_shard = shard;
     p->device = device; p->nv = nv; p->nv_local = nv; p->T = T; p->n_products = n_products; p->d = d; p->N = (uint64_t)1 << nv;
     auto bail = [&](int code) { sc_prover_destroy(p); return code; };
 #define TRY_P(expr)                                                                                        \
@@ -542,11 +546,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
         for (uint32_t j = 0; j < T; j++) p->tab0[j] = (uint32_t*)tables[j];
     } else {
         TRY_P(device_alloc((void**)&p->slab0, (size_t)T * N * elem, &p->slab0_bytes, device));
-        for (uint32_t j = 0; j < T; j++) {
-            p->tab0[j] = p->slab0 + (size_t)j * N * 8;
-            // deep copy of the caller's table (prover.rs:55-59); pageable or pinned source both work
-            TRY_P(cudaMemcpyAsync(p->tab0[j], tables[j], N * elem, cudaMemcpyHostToDevice, p->stream));
-        }
+        for (uint32_t j = 0; j < T; j++) p->tab0[j] = p->slab0 + (size_t)j * N * 8;  // filled by upload_tables below
     }
     // Two allocations for everything else (creation cost matters for one-shot proofs and the two GKR phases):
     // one device slab = ping-pong tables + all small arrays, one pinned+mapped host block.
@@ -640,8 +640,6 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
         if (any) {
             p->d_scaled = base + oScaled;
             TRY_P(cudaMemcpyAsync(p->d_scaled, p->h_scaled.data(), n_products, cudaMemcpyHostToDevice, p->stream));
-            int rc2 = prescale_tables(p);
-            if (rc2) return bail(rc2);
         }
     }
     if (d + 1 <= 32) {  // Lagrange weights + the nodes 0..d for the P(1)-from-claim shortcut: host table (cached per degree)
@@ -673,8 +671,14 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     p->ev.assign(2 * (size_t)nv, nullptr);  // CUDA events are created on demand (sc_prover_set_timing)
     p->round_ms.assign(nv, 0.f);
     p->randomness.reserve((size_t)nv * 4);
-    TRY_P(cudaStreamSynchronize(p->stream));  // uploads done: the caller may free/modify its buffers
+    TRY_P(cudaStreamSynchronize(p->stream));
 #undef TRY_P
+    if (!tables_on_device) {
+        // the deep copy of the caller's tables (prover.rs:55-59), pipelined with round 1 where the shape allows; returns when
+        // the caller may free / modify its buffers
+        int rc2 = upload_tables(p, tables);
+        if (rc2) return bail(rc2);
+    }
     *out = p;
     return SC_OK;
 }
@@ -693,6 +697,136 @@ int prescale_tables(sc_prover* p) {
     }
     return SC_OK;
 }
+
+// ---- table upload --------------------------------------------------------------------------------------------------
+// Pinned bounce slots for pageable sources (host_copy.h), shared by all handles of a device; an upload holds the mutex.
+constexpr size_t BOUNCE_SLOT_BYTES = (size_t)16 << 20;
+constexpr int BOUNCE_SLOTS = 4;
+struct Bounce {
+    std::mutex mu;
+    uint8_t* slot[BOUNCE_SLOTS] = {};
+    cudaEvent_t ev[BOUNCE_SLOTS] = {};
+    bool busy[BOUNCE_SLOTS] = {};
+    size_t k = 0;
+};
+Bounce g_bounce[64];
+
+bool host_pointer_is_pageable(const void* ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// dst (device) <- src (host) on stream s.  A pageable source is staged: the copy pool fills a pinned slot with
+// non-temporal stores while the DMA engine drains the previous one.
+cudaError_t h2d(Bounce* B, void* dst, const void* src, size_t bytes, cudaStream_t s) {
+    if (!B) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+    hcopy::Pool& pool = hcopy::Pool::get();
+    for (size_t off = 0; off < bytes; off += BOUNCE_SLOT_BYTES) {
+        const size_t len = bytes - off < BOUNCE_SLOT_BYTES ? bytes - off : BOUNCE_SLOT_BYTES;
+        const int k = (int)(B->k++ % BOUNCE_SLOTS);
+        cudaError_t e;
+        if (B->busy[k] && (e = cudaEventSynchronize(B->ev[k])) != cudaSuccess) return e;
+        pool.copy(B->slot[k], (const uint8_t*)src + off, len);
+        if ((e = cudaMemcpyAsync((uint8_t*)dst + off, B->slot[k], len, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(B->ev[k], s)) != cudaSuccess) return e;
+        B->busy[k] = true;
+    }
+    return cudaSuccess;
+}
+
+// Locks and (first time) allocates the device's bounce slots when any source table is pageable and large enough to matter.
+struct BounceLease {
+    Bounce* B = nullptr;
+    ~BounceLease() { release(); }
+    void release() {
+        if (B) B->mu.unlock();
+        B = nullptr;
+    }
+    cudaError_t acquire(const sc_prover* p, const uint64_t* const* tables) {
+        if (p->N * 32 < ((size_t)4 << 20) || getenv("SC_NO_BOUNCE")) return cudaSuccess;
+        bool pageable = false;
+        for (uint32_t j = 0; j < p->T && !pageable; j++) pageable = host_pointer_is_pageable(tables[j]);
+        if (!pageable) return cudaSuccess;
+        Bounce& b = g_bounce[p->device & 63];
+        b.mu.lock();
+        B = &b;
+        for (int k = 0; k < BOUNCE_SLOTS; k++) {
+            if (!b.slot[k]) {
+                cudaError_t e = cudaHostAlloc((void**)&b.slot[k], BOUNCE_SLOT_BYTES, cudaHostAllocDefault);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev[k], cudaEventDisableTiming);
+                if (e != cudaSuccess) { release(); return e; }
+            }
+            b.busy[k] = false;  // the previous upload synchronised its stream before it let go of the slots
+        }
+        return cudaSuccess;
+    }
+};
+
+// H2D of all tables into the pristine copies, then rewind to round 0 (prover_init's deep copy and sc_prover_load_tables).
+int upload_tables(sc_prover* p, const uint64_t* const* tables) {
+    CUDA_TRY(cudaSetDevice(p->device));
+    BounceLease lease;
+    CUDA_TRY(lease.acquire(p, tables));
+    // Pipelined path: round 1 needs no challenge, so it is summed chunk by chunk behind the copies (the upload of 1.5 GiB
+    // takes ~29 ms over PCIe; the 1.1 ms of round 1 disappear behind it).  One product with a deferred coefficient only
+    // (pre-scaled tables would have to be scaled before they are summed), single GPU, d + 1 <= 5 points, host finishing.
+    const unsigned long long tiles = p->N / 256;  // 64-row tiles of round 1 (128 pairs each)
+    const bool eager = p->r1_ok && p->host_post && !p->comm && !p->is_shard && !p->d_scaled && p->n_products == 1 && p->d + 1 <= (uint32_t)sck::MAX_NPTS &&
+                       tiles % EAGER_CHUNKS == 0 && tiles / EAGER_CHUNKS >= 1024 && !getenv("SC_NO_EAGER_R1");
+    if (!eager) {
+        for (uint32_t j = 0; j < p->T; j++) CUDA_TRY(h2d(lease.B, p->tab0[j], tables[j], p->N * 32, p->stream));
+        int rc = prescale_tables(p);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(p->stream));
+        return sc_prover_reset(p);
+    }
+    if (!p->copy_stream) CUDA_TRY(stream_acquire(&p->copy_stream, p->device));
+    for (auto& e : p->eager_ev)
+        if (!e) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    // the copies may only start once earlier work on the proving stream (a previous proof reading tab0) has finished
+    CUDA_TRY(cudaEventRecord(p->eager_ev[0], p->stream));
+    CUDA_TRY(cudaStreamWaitEvent(p->copy_stream, p->eager_ev[0], 0));
+    sc_prover_reset(p);
+    const uint32_t epoch = ++p->eager_epoch;
+    const size_t chunk_elems = p->N / EAGER_CHUNKS;
+    sck::RoundParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.tab_in = (const uint32_t* const*)p->d_ptr0;
+    rp.prod_offsets = p->d_offsets; rp.prod_indices = p->d_indices; rp.prod_first = p->d_first; rp.coeffs = p->d_coeffs;
+    rp.n_products = p->n_products; rp.n_tables = p->T; rp.defer_coeff = 1;
+    rp.n_pairs = chunk_elems / 2;
+    rp.partials = p->d_partials; rp.counter = p->d_counter;
+    rp.evals_out = p->d_evals; rp.canon_out = p->d_canon; rp.degree = p->d;
+    rp.tmaps = p->d_maps + (size_t)3 * p->T * sizeof(CUtensorMap);
+    rp.raw_out = 1;
+    rp.seq = epoch;
+    for (uint32_t c = 0; c < EAGER_CHUNKS; c++) {
+        for (uint32_t j = 0; j < p->T; j++)
+            CUDA_TRY(h2d(lease.B, p->tab0[j] + c * chunk_elems * 8, tables[j] + c * chunk_elems * 4, chunk_elems * 32, p->copy_stream));
+        CUDA_TRY(cudaEventRecord(p->eager_ev[c], p->copy_stream));
+        CUDA_TRY(cudaStreamWaitEvent(p->stream, p->eager_ev[c], 0));
+        rp.tile_base = (uint32_t)(c * (tiles / EAGER_CHUNKS));
+        rp.host_out = p->d_eager + (size_t)c * EAGER_SLOT_WORDS;
+        rp.host_flag = p->d_eager + (size_t)c * EAGER_SLOT_WORDS + sck::MAX_NPTS * 8;
+        cudaError_t e;
+        switch (p->d + 1) {
+            case 1: e = launch_round1_tma<1>(p, rp); break;
+            case 2: e = launch_round1_tma<2>(p, rp); break;
+            case 3: e = launch_round1_tma<3>(p, rp); break;
+            case 4: e = launch_round1_tma<4>(p, rp); break;
+            default: e = launch_round1_tma<5>(p, rp); break;
+        }
+        if (e != cudaSuccess) return fail(SC_ERR_CUDA, "round-1 chunk launch: %s", cudaGetErrorString(e));
+    }
+    CUDA_TRY(cudaStreamSynchronize(p->copy_stream));  // the caller's buffers are free again; the last chunk's sum may still run
+    p->eager_valid = true;
+    return SC_OK;
+}
+
 
 int sharded_round(sc_prover* p, const uint64_t* r);  // capi_multi.inc
 
@@ -1155,63 +1289,7 @@ int sc_prover_load_tables(sc_prover* p, const uint64_t* const* tables) {
     NEED_HANDLE(p);
     if (!tables) return fail(SC_ERR_BAD_INPUT, "null table list");
     if (!p->owns_tab0) return fail(SC_ERR_BAD_INPUT, "handle was created over caller-owned device tables");
-    CUDA_TRY(cudaSetDevice(p->device));
-    // Pipelined path: round 1 needs no challenge, so it is summed chunk by chunk behind the copies (the upload of 1.5 GiB
-    // takes ~29 ms over PCIe; the 1.1 ms of round 1 disappear behind it).  One product with a deferred coefficient only
-    // (pre-scaled tables would have to be scaled before they are summed), single GPU, d + 1 <= 5 points, host finishing.
-    const unsigned long long tiles = p->N / 256;  // 64-row tiles of round 1 (128 pairs each)
-    const bool eager = p->r1_ok && p->host_post && !p->comm && !p->d_scaled && p->n_products == 1 && p->d + 1 <= (uint32_t)sck::MAX_NPTS &&
-                       tiles % EAGER_CHUNKS == 0 && tiles / EAGER_CHUNKS >= 1024 && !getenv("SC_NO_EAGER_R1");
-    if (!eager) {
-        for (uint32_t j = 0; j < p->T; j++)
-            CUDA_TRY(cudaMemcpyAsync(p->tab0[j], tables[j], p->N * 32, cudaMemcpyHostToDevice, p->stream));
-        int rc = prescale_tables(p);
-        if (rc) return rc;
-        CUDA_TRY(cudaStreamSynchronize(p->stream));
-        return sc_prover_reset(p);
-    }
-    if (!p->copy_stream) CUDA_TRY(stream_acquire(&p->copy_stream, p->device));
-    for (auto& e : p->eager_ev)
-        if (!e) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    // the copies may only start once earlier work on the proving stream (a previous proof reading tab0) has finished
-    CUDA_TRY(cudaEventRecord(p->eager_ev[0], p->stream));
-    CUDA_TRY(cudaStreamWaitEvent(p->copy_stream, p->eager_ev[0], 0));
-    sc_prover_reset(p);
-    const uint32_t epoch = ++p->eager_epoch;
-    const size_t chunk_elems = p->N / EAGER_CHUNKS;
-    sck::RoundParams rp;
-    memset(&rp, 0, sizeof(rp));
-    rp.tab_in = (const uint32_t* const*)p->d_ptr0;
-    rp.prod_offsets = p->d_offsets; rp.prod_indices = p->d_indices; rp.prod_first = p->d_first; rp.coeffs = p->d_coeffs;
-    rp.n_products = p->n_products; rp.n_tables = p->T; rp.defer_coeff = 1;
-    rp.n_pairs = chunk_elems / 2;
-    rp.partials = p->d_partials; rp.counter = p->d_counter;
-    rp.evals_out = p->d_evals; rp.canon_out = p->d_canon; rp.degree = p->d;
-    rp.tmaps = p->d_maps + (size_t)3 * p->T * sizeof(CUtensorMap);
-    rp.raw_out = 1;
-    rp.seq = epoch;
-    for (uint32_t c = 0; c < EAGER_CHUNKS; c++) {
-        for (uint32_t j = 0; j < p->T; j++)
-            CUDA_TRY(cudaMemcpyAsync(p->tab0[j] + c * chunk_elems * 8, tables[j] + c * chunk_elems * 4, chunk_elems * 32, cudaMemcpyHostToDevice,
-                                     p->copy_stream));
-        CUDA_TRY(cudaEventRecord(p->eager_ev[c], p->copy_stream));
-        CUDA_TRY(cudaStreamWaitEvent(p->stream, p->eager_ev[c], 0));
-        rp.tile_base = (uint32_t)(c * (tiles / EAGER_CHUNKS));
-        rp.host_out = p->d_eager + (size_t)c * EAGER_SLOT_WORDS;
-        rp.host_flag = p->d_eager + (size_t)c * EAGER_SLOT_WORDS + sck::MAX_NPTS * 8;
-        cudaError_t e;
-        switch (p->d + 1) {
-            case 1: e = launch_round1_tma<1>(p, rp); break;
-            case 2: e = launch_round1_tma<2>(p, rp); break;
-            case 3: e = launch_round1_tma<3>(p, rp); break;
-            case 4: e = launch_round1_tma<4>(p, rp); break;
-            default: e = launch_round1_tma<5>(p, rp); break;
-        }
-        if (e != cudaSuccess) return fail(SC_ERR_CUDA, "round-1 chunk launch: %s", cudaGetErrorString(e));
-    }
-    CUDA_TRY(cudaStreamSynchronize(p->copy_stream));  // the caller's buffers are free again; the last chunk's sum may still run
-    p->eager_valid = true;
-    return SC_OK;
+    return upload_tables(p, tables);
 }
 
 int sc_prover_set_stream(sc_prover* p, void* cuda_stream) {
