@@ -209,6 +209,17 @@ SC_API int sc_prover_create_sharded(sc_prover **out, sc_comm *comm, uint32_t nv,
                              const uint64_t *const *shard_tables, uint32_t n_products, const uint64_t *coeffs,
                              const uint32_t *offsets, const uint32_t *indices);
 
+
+/* Single-process multi-GPU: the same sharded prover driven by ONE host process — what MLSumcheck::prove(&poly)
+ * (src/ml_sumcheck/mod.rs:42) needs to use several GPUs from one Rust process.  `tables` are the FULL host tables (2^nv
+ * elements each); rank r uploads elements [r*2^nv/n, (r+1)*2^nv/n) to device_ids[r] from its own host thread.  n_devices
+ * must be a power of two; the devices need peer access to each other (NVLink/NVSwitch), and a device may be listed more
+ * than once (ranks then share it).  The returned handle works with every sc_prover_* / sc_prove_round / sc_ml_prove call
+ * (sc_prover_set_stream excepted); n_devices == 1 gives an ordinary handle. */
+SC_API int sc_prover_create_multi(sc_prover **out, uint32_t nv, uint32_t n_tables, const uint64_t *const *tables,
+                                  uint32_t n_products, const uint64_t *coeffs, const uint32_t *offsets, const uint32_t *indices,
+                                  const int *device_ids, uint32_t n_devices);
+
 #ifdef __cplusplus
 }
 #endif

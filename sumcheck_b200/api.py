@@ -286,6 +286,11 @@ def _create(poly, device):
     T = len(poly.flattened_ml_extensions)
     tabs = (C.c_void_p * max(T, 1))(*[t.ctypes.data for t in poly.flattened_ml_extensions])
     h = C.c_void_p()
+    if isinstance(device, (list, tuple)):  # several GPUs driven by this one process (sc_prover_create_multi)
+        ids = (C.c_int * len(device))(*device)
+        _check(capi.lib().sc_prover_create_multi(C.byref(h), poly.num_variables, T, tabs, len(poly.products),
+                                                 _p64(coeffs) if len(poly.products) else None, _p32(offsets), _p32(indices), ids, len(device)))
+        return ProverState(h, poly)
     _check(capi.lib().sc_prover_create(C.byref(h), poly.num_variables, T, tabs, len(poly.products),
                                        _p64(coeffs) if len(poly.products) else None, _p32(offsets), _p32(indices), device))
     return ProverState(h, poly)
@@ -296,6 +301,8 @@ class IPForMLSumcheck:
 
     @staticmethod
     def prover_init(polynomial, device=0):  # prover.rs:49-69
+        """`device` is a CUDA device index, or a list of them: the tables are then sharded by the high hypercube bits over those
+        GPUs (one host thread per GPU inside the library) and the state behaves like a single-GPU one."""
         return _create(polynomial, device)
 
     @staticmethod

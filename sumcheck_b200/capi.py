@@ -60,6 +60,8 @@ SIGNATURES = {
     "sc_comm_destroy": (None, [C.c_void_p]),
     "sc_prover_create_sharded": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p),
                                            C.c_uint32, U64P, U32P, U32P]),
+    "sc_prover_create_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, U64P, U32P,
+                                         U32P, C.POINTER(C.c_int), C.c_uint32]),
     "sc_gkr_initialize_phase_one": (C.c_int, [C.c_uint32, C.c_uint64, U64P, U64P, U64P, U64P, C.c_int, U64P, U64P, U64P, U64P]),
     "sc_gkr_initialize_phase_two": (C.c_int, [C.c_uint32, C.c_uint64, U64P, U64P, U64P, C.c_int, U64P]),
     "sc_gkr_start_phase1_sumcheck": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, U64P, U64P, C.c_int]),

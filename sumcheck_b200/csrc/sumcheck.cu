@@ -279,6 +279,14 @@ struct sc_prover {
     sc_prover* sub = nullptr;  // replicated prover for the last rounds
     sc_prover* wait_on = nullptr;  // whose mapped result block the round just issued will signal (this or sub)
     uint32_t switch_round = 0;     // first global round run replicated
+    bool switched = false;         // ... and this proof has gathered the tables for it
+    bool host_done = false;        // the round just run left its message in h_evals / h_canon (host-side exchange)
+    uint32_t** d_peer_tabs = nullptr;  // [3][n_ranks][T] every rank's table pointers in each buffer, as seen from this device
+    std::vector<void*> ipc_opened;     // peer slabs mapped through CUDA IPC (multi-process)
+    // ---- single-process multi-GPU facade (sc_prover_create_multi): the shards, one comm and one worker thread per rank
+    std::vector<sc_prover*> group;
+    std::vector<struct sc_comm*> group_comms;
+    struct MultiWorkers* workers = nullptr;
     uint32_t *d_gather = nullptr, *d_evals_g = nullptr, *d_canon_g = nullptr, *d_sub_tabs = nullptr;
     std::vector<uint64_t> h_coeffs;
     // Pre-applied coefficients: h_scaled[k] = 1 when product k's coefficient lives in table scaled_table[k] (a table only
@@ -291,7 +299,7 @@ struct sc_prover {
     // Resident rounds (resident_kernel.cuh): set by run_rounds for the proof in flight
     uint32_t res_first = 0;            // first (1-based) round served by the resident kernel; 0 = none
     bool res_running = false;          // the kernel is on the GPU, waiting for fold constants
-    uint32_t res_seq0 = 0;             // sequence number of its first round
+    uint32_t res_seq0 = 0, res_last_seq = 0;  // sequence numbers of its first and last round
     unsigned long long res_max_pairs = 0;
     uint32_t *h_res = nullptr, *d_res = nullptr;  // mapped block: [64 x {limb,seq}] constants | [40 x {limb,seq}] sums | error | abort
     uint32_t* d_res_bcast = nullptr;   // device: [64 x {limb,seq}] + abort word
@@ -376,8 +384,17 @@ cudaError_t launch_round1_tma(sc_prover* p, const sck::RoundParams& rp) {
 }
 
 void set_exchange_params(sc_prover* p, sck::RoundParams& rp);  // capi_multi.inc
+uint32_t set_exchange_params_resident(sc_prover* p, sck::RoundParams& rp, uint32_t n_rounds);
 bool comm_failed(const sc_prover* p);
 void comm_clear_error(sc_prover* p);
+// single-process multi-GPU facade (capi_multi.inc)
+void multi_destroy(sc_prover* P);
+int multi_reset(sc_prover* P);
+int multi_load_tables(sc_prover* P, const uint64_t* const* tables);
+int multi_prove_round(sc_prover* P, const uint64_t* r_or_null, uint64_t* evals_out);
+int multi_ml_prove(sc_prover* P, sc_blake2b512_rng* rng, uint64_t* evals_out, uint64_t* randomness_out);
+int multi_table(const sc_prover* P, uint32_t j, uint64_t* out, uint64_t cap_elems, uint64_t* len_out);
+inline const sc_prover* lead(const sc_prover* p) { return (p && !p->group.empty()) ? p->group[0] : p; }
 
 // One protocol round on the device: (fold on r) + sums for all d+1 points.  Results land in d_evals / d_canon.
 int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
@@ -861,10 +878,17 @@ void host_finish_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
 
 // ---- resident rounds (resident_kernel.cuh) ---------------------------------------------------------------------------
 // First (1-based) round the resident kernel serves for a whole-proof call (run_rounds), or 0.
+bool comm_fused_exchange_ok(const sc_prover* p);  // capi_multi.inc: the sharded rounds of this handle run the fused peer-memory exchange
+int comm_device_share(const sc_prover* p);
+
 uint32_t resident_first_round(const sc_prover* p) {
-    if (p->res_max_pairs == 0 || p->comm || !p->host_post || !p->direct_results || p->d < 1 || p->d > (uint32_t)sck::MAX_NPTS || !p->d_lagrange || getenv("SC_TAIL"))
+    if (p->res_max_pairs == 0 || !p->host_post || !p->direct_results || p->d < 1 || p->d > (uint32_t)sck::MAX_NPTS || !p->d_lagrange || getenv("SC_TAIL"))
         return 0;
-    for (uint32_t i = 2; i <= p->nv_local; i++)
+    // sharded handle: the resident kernel serves the sharded rounds up to the switch (exchange of the partial sums inside the
+    // kernel); the replicated rounds after the switch run on the sub-prover's own resident launch
+    if (p->comm && !comm_fused_exchange_ok(p)) return 0;
+    const uint32_t last = p->comm ? p->switch_round - 1 : p->nv_local;
+    for (uint32_t i = 2; i <= last; i++)
         if (((unsigned long long)1 << (p->nv_local - i)) <= p->res_max_pairs) return i;
     return 0;
 }
@@ -872,6 +896,7 @@ uint32_t resident_first_round(const sc_prover* p) {
 // Enqueue the resident kernel behind the launch of round res_first - 1 (p->cur already names the buffer that round writes).
 int resident_launch(sc_prover* p) {
     const uint32_t first = p->res_first, nv = p->nv_local, d = p->d;
+    const uint32_t last = p->comm ? p->switch_round - 1 : nv;  // sharded: up to the switch to replicated rounds
     sck::ResidentParams q;
     memset(&q, 0, sizeof(q));
     sck::RoundParams& rp = q.rp;
@@ -881,9 +906,10 @@ int resident_launch(sc_prover* p) {
     rp.t0 = 0; rp.write_fold = 1; rp.skip1 = 1; rp.degree = d;
     q.ptrs[0] = p->d_ptr0; q.ptrs[1] = p->d_ptrA; q.ptrs[2] = p->d_ptrB;
     q.cur = p->cur;
-    q.n_rounds = nv - first + 1;
+    q.n_rounds = last - first + 1;
     q.n_pairs_first = (unsigned long long)1 << (nv - first);
     q.seq0 = p->seq + 1;
+    if (p->comm) q.mail_seq0 = set_exchange_params_resident(p, rp, q.n_rounds);
     q.h_consts = (const uint32_t*)((uint8_t*)p->d_res + RES_OFF_CONSTS);
     q.h_sums = (uint32_t*)((uint8_t*)p->d_res + RES_OFF_SUMS);
     q.h_error = (uint32_t*)((uint8_t*)p->d_res + RES_OFF_ERROR);
@@ -906,12 +932,18 @@ int resident_launch(sc_prover* p) {
     unsigned long long need = (q.n_pairs_first + sck::RES_THREADS - 1) / sck::RES_THREADS;
     unsigned long long cap = (unsigned long long)sck::resident_max_grid(d, p->device, g_dev[p->device].sms);
     if (cap * 2 > (unsigned long long)p->max_grid) cap = p->max_grid / 2;  // partials: [2][grid][NPTS][8]
+    // ranks sharing a device (sc_prover_create_multi with a repeated device id): their resident kernels wait for each other's
+    // partial sums, so ALL of them must fit on the device at once — next to the launch-per-round kernels of a rank that is
+    // still a round behind (half of the device is left to those)
+    if (comm_device_share(p) > 1) cap /= 2ull * (unsigned long long)comm_device_share(p);
+    if (cap < 1) cap = 1;
     const int grid = (int)(need < cap ? (need ? need : 1) : cap);
     cudaError_t e = sck::launch_resident(d, grid, q, p->stream);
     if (e != cudaSuccess) return fail(SC_ERR_CUDA, "resident kernel launch: %s", cudaGetErrorString(e));
     p->launches++;
     p->res_running = true;
     p->res_seq0 = q.seq0;
+    p->res_last_seq = q.seq0 + q.n_rounds - 1;
     return SC_OK;
 }
 
@@ -925,19 +957,21 @@ void resident_abort(sc_prover* p) {
 }
 
 // One round served by the resident kernel: prove_round's state machine, then fold constants out / raw sums in.
-int resident_round(sc_prover* p, const uint64_t* r) {
+// `w` is the handle whose kernel is on the GPU: p itself, or the replicated sub-prover of a sharded p.
+int resident_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
     p->randomness.insert(p->randomness.end(), r, r + 4);  // prover.rs:82
     p->round += 1;
     if (p->round > p->nv) return fail(SC_ERR_PANIC_NOT_ACTIVE, "Prover is not active");
-    const uint32_t seq = ++p->seq, d = p->d;
-    const bool prof = p->d_res_prof != nullptr;
+    if (w != p) w->round += 1;
+    const uint32_t seq = ++w->seq, d = p->d;
+    const bool prof = w->d_res_prof != nullptr;
     auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
     const double h0 = prof ? now_us() : 0;
     // C[k] = r * 2^(32k+64) mod p as plain integers (fr.cuh fold_const): Montgomery-multiply r by the raw 2^(32k+64) mod p
     static const hfr::F X7 = {{0x355094eacaaf6b13ULL, 0xf6b10cb369a568efULL, 0xe2c926a640cc3869ULL, 0x736a6d3bed269aadULL}};  // 2^288 mod p
     hfr::F rr;
     memcpy(&rr, r, 32);
-    uint64_t* hc = (uint64_t*)((uint8_t*)p->h_res + RES_OFF_CONSTS);
+    uint64_t* hc = (uint64_t*)((uint8_t*)w->h_res + RES_OFF_CONSTS);
     for (int k = 0; k < 8; k++) {
         hfr::F x = {{0, 0, 0, 0}};
         if (k < 6) x.l[(k + 2) / 2] = (uint64_t)1 << (32 * ((k + 2) & 1));
@@ -951,49 +985,50 @@ int resident_round(sc_prover* p, const uint64_t* r) {
     }
     const double h1 = prof ? now_us() : 0;
     // wait for the d raw sums: every limb arrives as one {limb, seq} word
-    const uint64_t* hs = (const uint64_t*)((uint8_t*)p->h_res + RES_OFF_SUMS);
+    const uint64_t* hs = (const uint64_t*)((uint8_t*)w->h_res + RES_OFF_SUMS);
     const uint32_t n_words = d * 8;
     SpinWait sw;
-    for (uint32_t w = 0; w < n_words; w++) {
+    for (uint32_t k = 0; k < n_words; k++) {
         uint64_t v;
-        while (((v = __atomic_load_n(hs + w, __ATOMIC_RELAXED)) >> 32) != seq) {
+        while (((v = __atomic_load_n(hs + k, __ATOMIC_RELAXED)) >> 32) != seq) {
             sw.pause();
             if (sw.check_now()) {
-                if (*(volatile uint32_t*)((uint8_t*)p->h_res + RES_OFF_ERROR)) {
-                    p->res_running = false;
+                if (*(volatile uint32_t*)((uint8_t*)w->h_res + RES_OFF_ERROR)) {
+                    w->res_running = false;
                     return fail(p->comm ? SC_ERR_COMM : SC_ERR_CUDA, "resident kernel gave up waiting (host constants or a peer GPU did not arrive in time)");
                 }
-                cudaError_t q = cudaStreamQuery(p->stream);
-                if (q != cudaSuccess && q != cudaErrorNotReady) { p->res_running = false; return fail(SC_ERR_CUDA, "resident kernel failed: %s", cudaGetErrorString(q)); }
-                if (q == cudaSuccess && (__atomic_load_n(hs + w, __ATOMIC_RELAXED) >> 32) != seq) {
-                    p->res_running = false;
+                cudaError_t q = cudaStreamQuery(w->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) { w->res_running = false; return fail(SC_ERR_CUDA, "resident kernel failed: %s", cudaGetErrorString(q)); }
+                if (q == cudaSuccess && (__atomic_load_n(hs + k, __ATOMIC_RELAXED) >> 32) != seq) {
+                    w->res_running = false;
                     return fail(SC_ERR_CUDA, "resident kernel ended without publishing round %u", p->round);
                 }
             }
         }
-        p->h_result[w] = (uint32_t)v;
+        w->h_result[k] = (uint32_t)v;
     }
     __sync_synchronize();
     const double h2 = prof ? now_us() : 0;
-    p->raw_npts = d;
-    p->used_skip1 = true;
-    host_finish_round(p, p, r);
+    w->raw_npts = d;
+    w->used_skip1 = true;
+    host_finish_round(p, w, r);
     memcpy(p->h_prev.data(), p->h_evals, (size_t)(d + 1) * 32);
-    p->cur = (p->cur == 1) ? 2 : 1;
+    w->cur = (w->cur == 1) ? 2 : 1;
+    if (p->comm && comm_failed(p)) { w->res_running = false; return fail(SC_ERR_COMM, "a peer GPU did not deliver its partial sums in time"); }
     if (prof) {
-        double* h = p->res_host_us[(p->round - p->res_first) & 63];
+        double* h = w->res_host_us[(seq - w->res_seq0) & 63];
         h[0] = h1 - h0; h[1] = h2 - h1; h[2] = now_us() - h2;
-        if (p->round == p->nv) {
-            cudaStreamSynchronize(p->stream);
+        if (seq == w->res_last_seq) {
+            cudaStreamSynchronize(w->stream);
             long long hp[64 * 4];
-            cudaMemcpy(hp, p->d_res_prof, sizeof(hp), cudaMemcpyDeviceToHost);
-            for (uint32_t k = 0; k + p->res_first <= p->nv && k < 64; k++)
+            cudaMemcpy(hp, w->d_res_prof, sizeof(hp), cudaMemcpyDeviceToHost);
+            for (uint32_t k = 0; k <= w->res_last_seq - w->res_seq0 && k < 64; k++)
                 fprintf(stderr, "resident round %u: device wait %lld accumulate %lld reduce %lld publish %lld cycles | host consts %.2f wait %.2f finish %.2f us\n",
-                        p->res_first + k, hp[k * 4], hp[k * 4 + 1], hp[k * 4 + 2], hp[k * 4 + 3], p->res_host_us[k][0], p->res_host_us[k][1], p->res_host_us[k][2]);
+                        p->round - (w->res_last_seq - w->res_seq0) + k, hp[k * 4], hp[k * 4 + 1], hp[k * 4 + 2], hp[k * 4 + 3], w->res_host_us[k][0], w->res_host_us[k][1], w->res_host_us[k][2]);
         }
     }
     p->res_rounds++;
-    if (p->round == p->nv) p->res_running = false;  // the kernel has published its last round and leaves by itself
+    if (seq == w->res_last_seq) w->res_running = false;  // the kernel has published its last round and leaves by itself
     p->out_evals = nullptr;  // the message of a resident round lives on the host only
     p->out_canon = nullptr;
     return SC_OK;
@@ -1058,6 +1093,10 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
     }
     if (rc) return rc;
     if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));
+    if (p->host_done) {  // the message is already complete on the host
+        p->host_done = false;
+        return SC_OK;
+    }
     if (p->res_first && p->round + 1 == p->res_first) {
         // the next round is the first resident one: queue the kernel now, so that it is already polling when this
         // round's challenge has been drawn
@@ -1179,6 +1218,28 @@ int run_tail(sc_prover* p, b2::State* st, uint32_t first, const uint64_t* r, uin
     return SC_OK;
 }
 
+int switch_to_replicated(sc_prover* p);  // capi_multi.inc
+
+// One round of a whole-proof call: the resident kernel when it is serving this round, a launch otherwise.
+int round_dispatch(sc_prover* p, const uint64_t* r) {
+    const uint32_t i = p->round + 1;  // the (global) round about to run
+    if (!p->comm || i < p->switch_round)
+        return (p->res_first && i >= p->res_first) ? resident_round(p, p, r) : prove_round_impl(p, r, true);
+    // sharded handle, replicated rounds: the sub-prover continues the same proof on the gathered (small) tables
+    if (i == p->switch_round) {
+        int rc = switch_to_replicated(p);
+        if (rc) return rc;
+        sc_prover* w = p->sub;
+        w->res_first = resident_first_round(w) == 2 ? 2 : 0;  // every replicated round, or none
+        if (w->res_first) {
+            rc = resident_launch(w);
+            if (rc) return rc;
+        }
+    }
+    if (p->sub->res_first) return resident_round(p, p->sub, r);
+    return prove_round_impl(p, r, true);
+}
+
 // The round loop shared by MLSumcheck (mod.rs:59-64) and the two GKR phases (gkr mod.rs:111-119, 126-133):
 // prove_round -> rng.feed(&prover_msg) -> sample_round.  challenges_out: nv*4 u64.
 int run_rounds(sc_prover* p, b2::State* st, uint64_t* evals_out, uint64_t* challenges_out) {
@@ -1193,6 +1254,7 @@ int run_rounds(sc_prover* p, b2::State* st, uint64_t* evals_out, uint64_t* chall
     auto bail = [&](int rc) {
         p->timing = false;
         resident_abort(p);
+        if (p->sub) { resident_abort(p->sub); p->sub->res_first = 0; }
         p->res_first = 0;
         return rc;
     };
@@ -1202,7 +1264,7 @@ int run_rounds(sc_prover* p, b2::State* st, uint64_t* evals_out, uint64_t* chall
             if (rc) return bail(rc);
             break;
         }
-        int rc = (p->res_first && i + 1 >= p->res_first) ? resident_round(p, r) : prove_round_impl(p, have_r ? r : nullptr, true);
+        int rc = round_dispatch(p, have_r ? r : nullptr);
         if (rc) return bail(rc);
         memcpy(evals_out + (size_t)i * (d + 1) * 4, p->h_evals, (size_t)(d + 1) * 32);
         memcpy(msg.data() + 8, p->h_canon, (size_t)(d + 1) * 32);
@@ -1212,6 +1274,7 @@ int run_rounds(sc_prover* p, b2::State* st, uint64_t* evals_out, uint64_t* chall
         memcpy(challenges_out + (size_t)i * 4, r, 32);
     }
     p->res_first = 0;
+    if (p->sub) p->sub->res_first = 0;
     p->timing = false;
     if (p->want_timing) {
         cudaStreamSynchronize(p->stream);
@@ -1252,10 +1315,13 @@ int sc_prover_create_device(sc_prover** out, uint32_t nv, uint32_t n_tables, con
 
 void sc_prover_destroy(sc_prover* p) {
     if (!p) return;
+    if (!p->group.empty() || p->workers) { multi_destroy(p); return; }
     cudaSetDevice(p->device);
     resident_abort(p);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->sub) { p->sub->stream = p->sub->own_stream; sc_prover_destroy(p->sub); cudaSetDevice(p->device); }
+    for (void* q : p->ipc_opened) cudaIpcCloseMemHandle(q);
+    cudaFree(p->d_peer_tabs);
     cudaFree(p->d_gather); cudaFree(p->d_evals_g); cudaFree(p->d_canon_g); cudaFree(p->d_sub_tabs);
     if (p->owns_tab0) device_free(p->slab0, p->slab0_bytes, p->device);
     cudaFree(p->d_res_prof);
@@ -1274,6 +1340,7 @@ void sc_prover_destroy(sc_prover* p) {
 
 int sc_prover_reset(sc_prover* p) {
     NEED_HANDLE(p);
+    if (!p->group.empty()) return multi_reset(p);
     p->round = 0;
     p->cur = 0;
     p->randomness.clear();
@@ -1281,6 +1348,7 @@ int sc_prover_reset(sc_prover* p) {
     p->tc_rounds = 0;
     p->res_rounds = 0;
     p->eager_valid = false;  // a pre-computed first round belongs to the proof that follows its upload only
+    p->switched = false;
     if (p->comm) comm_clear_error(p);  // a timed-out exchange invalidated the previous proof, not the communicator
     return SC_OK;
 }
@@ -1288,12 +1356,14 @@ int sc_prover_reset(sc_prover* p) {
 int sc_prover_load_tables(sc_prover* p, const uint64_t* const* tables) {
     NEED_HANDLE(p);
     if (!tables) return fail(SC_ERR_BAD_INPUT, "null table list");
+    if (!p->group.empty()) return multi_load_tables(p, tables);
     if (!p->owns_tab0) return fail(SC_ERR_BAD_INPUT, "handle was created over caller-owned device tables");
     return upload_tables(p, tables);
 }
 
 int sc_prover_set_stream(sc_prover* p, void* cuda_stream) {
     NEED_HANDLE(p);
+    if (!p->group.empty()) return fail(SC_ERR_BAD_INPUT, "a multi-device handle runs on its own per-device streams");
     CUDA_TRY(cudaSetDevice(p->device));
     CUDA_TRY(cudaStreamSynchronize(p->stream));
     p->stream = cuda_stream ? (cudaStream_t)cuda_stream : p->own_stream;
@@ -1303,6 +1373,7 @@ int sc_prover_set_stream(sc_prover* p, void* cuda_stream) {
 int sc_prove_round(sc_prover* p, const uint64_t* r_or_null, uint64_t* evals_out) {
     NEED_HANDLE(p);
     if (!evals_out) return fail(SC_ERR_BAD_INPUT, "null output buffer");
+    if (!p->group.empty()) return multi_prove_round(p, r_or_null, evals_out);
     int rc = prove_round_impl(p, r_or_null, true);
     if (rc) return rc;
     memcpy(evals_out, p->h_evals, (size_t)(p->d + 1) * 32);
@@ -1311,9 +1382,10 @@ int sc_prove_round(sc_prover* p, const uint64_t* r_or_null, uint64_t* evals_out)
 
 uint32_t sc_prover_max_multiplicands(const sc_prover* p) { return p ? p->d : 0; }
 uint32_t sc_prover_num_vars(const sc_prover* p) { return p ? p->nv : 0; }
-uint32_t sc_prover_round(const sc_prover* p) { return p ? p->round : 0; }
+uint32_t sc_prover_round(const sc_prover* p) { return p ? lead(p)->round : 0; }
 uint32_t sc_prover_randomness(const sc_prover* p, uint64_t* out, uint32_t cap) {
     if (!p) return 0;
+    p = lead(p);
     uint32_t n = (uint32_t)(p->randomness.size() / 4);
     uint32_t c = n < cap ? n : cap;
     if (out && c) memcpy(out, p->randomness.data(), (size_t)c * 32);
@@ -1323,6 +1395,7 @@ uint32_t sc_prover_randomness(const sc_prover* p, uint64_t* out, uint32_t cap) {
 int sc_prover_push_randomness(sc_prover* p, const uint64_t r[4]) {
     NEED_HANDLE(p);
     if (!r) return fail(SC_ERR_BAD_INPUT, "null challenge");
+    for (sc_prover* q : p->group) q->randomness.insert(q->randomness.end(), r, r + 4);
     p->randomness.insert(p->randomness.end(), r, r + 4);
     return SC_OK;
 }
@@ -1330,6 +1403,7 @@ int sc_prover_push_randomness(sc_prover* p, const uint64_t r[4]) {
 int sc_prover_table(const sc_prover* p, uint32_t j, uint64_t* out, uint64_t cap_elems, uint64_t* len_out) {
     NEED_HANDLE(p);
     if (j >= p->T) return fail(SC_ERR_BAD_INPUT, "table %u out of range", j);
+    if (!p->group.empty()) return multi_table(p, j, out, cap_elems, len_out);
     // after round i >= 2 the tables have been folded i-1 times
     if (p->comm && p->round >= p->switch_round) {  // replicated rounds: the full (small) tables live on the sub-prover
         if (!p->sub) return fail(SC_ERR_BAD_INPUT, "sharded prover: no replicated state yet");
@@ -1371,6 +1445,7 @@ int sc_prover_table(const sc_prover* p, uint32_t j, uint64_t* out, uint64_t cap_
 int sc_ml_prove(sc_prover* p, sc_blake2b512_rng* rng, uint64_t* evals_out, uint64_t* randomness_out) {
     NEED_HANDLE(p);
     if (!rng || !evals_out) return fail(SC_ERR_BAD_INPUT, "null rng or output buffer");
+    if (!p->group.empty()) return multi_ml_prove(p, rng, evals_out, randomness_out);
     if (p->round != 0) return fail(SC_ERR_BAD_INPUT, "sc_ml_prove needs a prover at round 0 (got %u)", p->round);
     b2::State* st = (b2::State*)rng;
     uint8_t info[16];
@@ -1430,13 +1505,14 @@ void sc_synth_table_at(uint64_t* out, uint64_t first_elem, uint64_t n_elems, uin
 
 uint32_t sc_prover_round_times_ms(const sc_prover* p, float* out, uint32_t cap) {
     if (!p) return 0;
+    p = lead(p);
     uint32_t c = p->nv < cap ? p->nv : cap;
     if (out && c) memcpy(out, p->round_ms.data(), c * sizeof(float));
     return p->nv;
 }
-uint64_t sc_prover_launch_count(const sc_prover* p) { return p ? p->launches : 0; }
-uint64_t sc_prover_tc_round_count(const sc_prover* p) { return p ? p->tc_rounds : 0; }
-uint64_t sc_prover_resident_round_count(const sc_prover* p) { return p ? p->res_rounds : 0; }
+uint64_t sc_prover_launch_count(const sc_prover* p) { return p ? lead(p)->launches : 0; }
+uint64_t sc_prover_tc_round_count(const sc_prover* p) { return p ? lead(p)->tc_rounds : 0; }
+uint64_t sc_prover_resident_round_count(const sc_prover* p) { return p ? lead(p)->res_rounds : 0; }
 
 void sc_release_cached_memory(void) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -1466,6 +1542,13 @@ int sc_fr_interpolate(const uint64_t* evals, uint32_t n_evals, const uint64_t r[
 }
 int sc_prover_set_timing(sc_prover* p, int enabled) {
     NEED_HANDLE(p);
+    if (!p->group.empty()) {
+        for (sc_prover* q : p->group) {
+            int rc = sc_prover_set_timing(q, enabled);
+            if (rc) return rc;
+        }
+        return SC_OK;
+    }
     p->want_timing = enabled != 0;
     if (p->want_timing) {
         CUDA_TRY(cudaSetDevice(p->device));

@@ -77,26 +77,133 @@ def ml_prove_sharded(comm, nv, shard_tables, products):
     return evals, st
 
 
-def bench_main(args, nv, d, T, METRIC, UNIT, field_sums, algorithmic_bytes, ClockSampler):
-    """bench.py body for N > 1 (launched by torchrun): strong scaling of ONE nv-variable proof over N GPUs."""
+def bench_main(args, cfg, nv, B):
+    """bench.py body for N > 1: strong scaling of ONE nv-variable proof over N GPUs.  Launched by torchrun (one process per
+    GPU, WORLD_SIZE > 1) or, with --single-process, as one process driving all N GPUs (sc_prover_create_multi).
+    B = the bench module (workload names, field_sums, ClockSampler ...)."""
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return _bench_torchrun(args, cfg, nv, B)
+    return _bench_single_process(args, cfg, nv, B)
+
+
+def _oracle_proof(cfg, nv, B):
+    """The unsharded CPU oracle on the same synthetic inputs (all host threads): what every bench line is compared with."""
+    from oracle import oracle as orc
+    from .synth import synth_table_fast
+    orc.set_threads(os.cpu_count() or 1)
+    tabs, prods, _ = B.ml_inputs(cfg, nv, synth_table_fast)
+    t0 = time.perf_counter()
+    want = orc.ml_prove(orc.Poly(nv, tabs, prods))[0]
+    return want, time.perf_counter() - t0
+
+
+def _line(B, cfg, nv, d, T, world, args, ms_step, step_ms, round_ms, launches, e2e_ms, e2e_call, h2d, clocks, how, extra):
+    fs = B.field_sums(nv, d)
+    peak, src = B.peak_hbm()
+    nv_l = nv - (world.bit_length() - 1)
+    fold_bytes = sum(B.algorithmic_bytes(nv_l, T, i) for i in range(2, nv_l + 1))  # per GPU
+    fold_ms = float(round_ms[1:nv_l].sum())
+    ach = fold_bytes / (fold_ms * 1e-3) / 1e9 if fold_ms > 0 else 0.0
+    total_bytes = 32 * T * (4 * (1 << nv) - 6)
+    line = {
+        "metric": B.metric_name(cfg), "value": fs / (ms_step * 1e-3), "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32x8 Montgomery (mod p, 255-bit)", "data": "synthetic",
+        "config": {"workload": B.workload_name(cfg, nv), "sharding": f"tables sharded by the high {world.bit_length() - 1} hypercube bits over {world} GPUs; " + how,
+                   "cache": f"per-GPU shard {T * ((1 << nv) // world) * 32 / 2**20:.0f} MiB, re-read from HBM every step",
+                   "median_ms_per_step": B.median(step_ms), "round_ms_rank0": [round(float(x), 4) for x in round_ms]},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "kernel": "sck::round_tc_kernel<3> / resident_kernel<3> on rank 0's shard (fold rounds up to the switch, incl. the fused peer-memory exchange), per GPU",
+                     "peak_source": src,
+                     "whole_proof": {"algorithmic_bytes": total_bytes, "achieved_per_gpu": total_bytes / world / (ms_step * 1e-3) / 1e9,
+                                     "frac": total_bytes / world / (ms_step * 1e-3) / 1e9 / peak}},
+        "e2e": {"value": fs / (B.median(e2e_ms) * 1e-3), "unit": B.UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": nv * (d + 1) * 32 * world, "ms_per_step": B.median(e2e_ms), "call": e2e_call},
+        "gpu_launches": int(launches) * args.steps * world, "clocks": clocks,
+    }
+    line.update(extra)
+    return line
+
+
+def _bench_single_process(args, cfg, nv, B):
+    import torch
+
+    from .synth import synth_table_fast
+    world = args.gpus
+    _, _, n_products, m = B.CONFIGS[cfg]
+    d, T = m, n_products * m
+    tabs, prods, _ = B.ml_inputs(cfg, nv, synth_table_fast)  # full tables, pageable
+    poly = api.ListOfProductsOfPolynomials.new(nv)
+    for c, ix in prods:
+        poly.add_product([tabs[j] for j in ix], c)
+    devs = list(range(world))
+    st = api.IPForMLSumcheck.prover_init(poly, device=devs)
+    evals = np.zeros((nv, d + 1, 4), dtype=np.uint64)
+
+    def prove():
+        st.reset()
+        st.prove_into(api.Blake2b512Rng.setup(), evals)
+
+    for _ in range(max(args.warmup, 3)):
+        prove()
+    sampler = B.ClockSampler(0)
+    sampler.start()
+    for dv in devs:
+        torch.cuda.synchronize(dv)
+    step_ms = []
+    for _ in range(args.steps):  # the call is synchronous (returns with the proof on the host): wall clock around it
+        t0 = time.perf_counter()
+        prove()
+        step_ms.append((time.perf_counter() - t0) * 1e3)
+    ms_step = sum(step_ms) / len(step_ms)
+    st.set_timing(True)
+    prove()
+    st.set_timing(False)
+    round_ms = st.round_times_ms().astype(np.float64)
+    launches = st.launch_count()
+    first = evals.copy()
+    e2e_ms, out = [], np.zeros_like(evals)
+    for k in range(args.steps + 1):  # the drop-in call over N GPUs: create (every rank uploads its slice) + prove + destroy
+        t0 = time.perf_counter()
+        s2 = api.IPForMLSumcheck.prover_init(poly, device=devs)
+        s2.prove_into(api.Blake2b512Rng.setup(), out)
+        del s2
+        if k:
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    clocks = sampler.stop()
+    extra = {}
+    ok = np.array_equal(first, out)
+    if not args.no_cpu_baseline:
+        want, cpu_s = _oracle_proof(cfg, nv, B)
+        ok = ok and np.array_equal(first, want)
+        extra["cpu_baseline"] = {"value": B.field_sums(nv, d) / cpu_s, "unit": B.UNIT, "cores": os.cpu_count(), "kind": "port",
+                                 "sample": "full workload, one proof, all host threads (OpenMP restatement of the rayon schedule)"}
+        extra["parity"] = "bit-exact vs oracle" if ok else "MISMATCH vs oracle"
+    line = _line(B, cfg, nv, d, T, world, args, ms_step, step_ms, round_ms, launches, e2e_ms,
+                 "sc_prover_create_multi + sc_ml_prove + destroy: pageable caller tables, one process, one host thread per GPU",
+                 T * (1 << nv) * 32, clocks, "ONE process, one host thread per GPU, exchange of the d partial sums fused into the round kernels (peer memory)", extra)
+    print(json.dumps(line), flush=True)
+    if not ok:
+        raise SystemExit("parity check failed")
+
+
+def _bench_torchrun(args, cfg, nv, B):
     import torch
     import torch.distributed as dist
 
     from .synth import synth_table_fast
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = int(os.environ.get("LOCAL_RANK", rank))
+    _, _, n_products, m = B.CONFIGS[cfg]
+    d, T = m, n_products * m
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     comm = Comm(broadcast_unique_id(dist, rank, torch.device("cuda", dev)), rank, world, dev)
     lo, hi = shard_range(nv, world, rank)
     n_loc = hi - lo
     # this rank's shard of the same synthetic tables the 1-GPU run uses (counter-based generator: any slice is cheap)
-    host = [torch.empty((n_loc, 4), dtype=torch.int64, pin_memory=True) for _ in range(T)]
-    tabs = [h.numpy().view(np.uint64) for h in host]
-    for j in range(T):
-        synth_table_fast(n_loc, 0x5C0300 + j, out=tabs[j], first=lo)
-    coeff = synth_table_fast(1, 0x5C03FF)[0]
-    st = prover_init_sharded(comm, nv, tabs, [(coeff, list(range(T)))])
+    tabs, prods, _ = B.ml_inputs(cfg, nv, synth_table_fast, first=lo, count=n_loc)  # pageable
+    st = prover_init_sharded(comm, nv, tabs, prods)
     stream = torch.cuda.current_stream()
     st.set_stream(stream.cuda_stream)
     evals = np.zeros((nv, d + 1, 4), dtype=np.uint64)
@@ -111,24 +218,26 @@ def bench_main(args, nv, d, T, METRIC, UNIT, field_sums, algorithmic_bytes, Cloc
 
     for _ in range(max(args.warmup, 3)):
         prove()
-    sampler = ClockSampler(dev)
+    sampler = B.ClockSampler(dev)
     if rank == 0:
         sampler.start()
 
     def timed(fn):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         dist.barrier()
         torch.cuda.synchronize()
-        e0.record(stream)
-        for _ in range(args.steps):
+        ev[0].record(stream)
+        for k in range(args.steps):
             fn()
-        e1.record(stream)
+            ev[k + 1].record(stream)
         torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=f"cuda:{dev}")
+        per = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+        t = torch.tensor([ev[0].elapsed_time(ev[args.steps]) / args.steps] + per, device=f"cuda:{dev}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
-        return float(t.item())
+        t = t.cpu().tolist()
+        return t[0], t[1:]
 
-    ms_step = timed(prove)
+    ms_step, step_ms = timed(prove)
     st.set_timing(True)
     prove()
     st.set_timing(False)
@@ -136,37 +245,30 @@ def bench_main(args, nv, d, T, METRIC, UNIT, field_sums, algorithmic_bytes, Cloc
     launches = st.launch_count()
     first = evals.copy()
     prove_e2e()
-    ms_e2e = timed(prove_e2e)
+    _, e2e_ms = timed(prove_e2e)
     same = torch.tensor(np.frombuffer(first.tobytes(), dtype=np.int64).copy(), device=f"cuda:{dev}")
     ref = same.clone()
     dist.broadcast(ref, src=0)
-    agree = torch.tensor([int(torch.equal(same, ref))], device=f"cuda:{dev}")
+    agree = torch.tensor([int(torch.equal(same, ref)) * int(np.array_equal(first, evals))], device=f"cuda:{dev}")
     dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+    ok = bool(agree.item())
     if rank == 0:
         clocks = sampler.stop()
-        fs = field_sums(nv, d)
-        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        pk = os.path.join(root, "MEASURED_PEAKS.json")
-        peak, src = (json.load(open(pk))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if os.path.exists(pk) else (6650.0, "fallback")
-        nv_l = nv - (world.bit_length() - 1)
-        fold_bytes = sum(algorithmic_bytes(nv_l, T, i) for i in range(2, nv_l + 1))  # per GPU
-        fold_ms = float(round_ms[1:nv_l].sum())
-        ach = fold_bytes / (fold_ms * 1e-3) / 1e9
-        line = {
-            "metric": METRIC, "value": fs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u32x8 Montgomery (mod p, 255-bit)", "data": "synthetic",
-            "config": {"workload": f"MLSumcheck prove nv={nv} deg={d} T={T}, 1 product (BASELINE config 3), tables sharded by the high "
-                                   f"{world.bit_length() - 1} hypercube bits over {world} GPUs, per-round exchange of the d+1 partial sums fused into the round kernel (NVLink peer memory)",
-                       "cache": f"per-GPU shard {T * n_loc * 32 / 2**20:.0f} MiB, re-read from HBM every step",
-                       "round_ms_rank0": [round(float(x), 4) for x in round_ms], "ranks_agree": bool(agree.item())},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "kernel": "sck::round_tc_kernel<3> / round_kernel<3,true> on rank 0's shard (TMA + tcgen05.mma fold for rounds with >= 2^14 pairs per shard; incl. the fused peer-memory exchange), sharded rounds aggregated",
-                         "peak_source": src},
-            "e2e": {"value": fs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": T * n_loc * 32 * world,
-                    "d2h_bytes_per_step": nv * (d + 1) * 32 * 2 * world, "ms_per_step": ms_e2e},
-            "gpu_launches": int(launches) * args.steps * world, "clocks": clocks,
-        }
+        extra = {}
+        if not args.no_cpu_baseline:  # rank 0 proves the UNSHARDED polynomial on the CPU oracle and compares bit for bit
+            want, cpu_s = _oracle_proof(cfg, nv, B)
+            ok = ok and np.array_equal(first, want)
+            extra["cpu_baseline"] = {"value": B.field_sums(nv, d) / cpu_s, "unit": B.UNIT, "cores": os.cpu_count(), "kind": "port",
+                                     "sample": "full workload, one proof, all host threads (OpenMP restatement of the rayon schedule)"}
+            extra["parity"] = ("bit-exact vs oracle (all ranks hold rank 0's proof)" if ok else "MISMATCH vs oracle")
+        else:
+            extra["parity"] = "ranks agree (oracle comparison skipped)" if ok else "RANKS DISAGREE"
+        line = _line(B, cfg, nv, d, T, world, args, ms_step, step_ms, round_ms, launches, e2e_ms,
+                     "sc_prover_load_tables (every rank re-uploads its pageable shard) + sc_ml_prove on one sharded handle per rank",
+                     T * n_loc * 32 * world, clocks,
+                     "one process per GPU, per-round exchange of the d partial sums fused into the round kernels (NVLink peer memory)", extra)
         print(json.dumps(line), flush=True)
     comm.close()
     dist.destroy_process_group()
+    if rank == 0 and not ok:
+        raise SystemExit("parity check failed")
