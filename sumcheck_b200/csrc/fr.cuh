@@ -242,6 +242,50 @@ static __device__ __noinline__ Fr mul_round_const_outlined(const uint32_t* C, Fr
 #define FR_MUL_ROUND_CONST(C, d) fr::mul_round_const(C, d)
 #endif
 
+// ILP forms for latency-bound kernels (resident rounds): ONE out-of-line routine works on several independent operands, so
+// ptxas interleaves their carry chains (a lone warp on a scheduler otherwise waits ~4 cycles between dependent IMAD.WIDE).
+// fold2: the two folds of one table row; mul_lazy_n: the N evaluation points of one multiplicand.
+struct Fr2 {
+    Fr a, b;
+};
+#ifdef FR_COMPACT
+static __device__ __noinline__ Fr2 mul_round_const_x2(const uint32_t* C, Fr d0, Fr d1) {
+    Fr2 r;
+    r.a = mul_round_const(C, d0);
+    r.b = mul_round_const(C, d1);
+    return r;
+}
+template <int N>
+struct FrN {
+    Fr v[N];
+};
+template <int N>
+static __device__ __noinline__ FrN<N> mul_lazy_n(FrN<N> a, FrN<N> b) {
+    FrN<N> r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = mul_lazy_impl(a.v[i], b.v[i]);
+    return r;
+}
+#else
+__device__ __forceinline__ Fr2 mul_round_const_x2(const uint32_t* C, const Fr& d0, const Fr& d1) {
+    Fr2 r;
+    r.a = mul_round_const(C, d0);
+    r.b = mul_round_const(C, d1);
+    return r;
+}
+template <int N>
+struct FrN {
+    Fr v[N];
+};
+template <int N>
+__device__ __forceinline__ FrN<N> mul_lazy_n(const FrN<N>& a, const FrN<N>& b) {
+    FrN<N> r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = mul_lazy_impl(a.v[i], b.v[i]);
+    return r;
+}
+#endif
+
 // ---- lazily reduced inner products -----------------------------------------------------------------------------
 // A WideAcc holds an UNREDUCED integer sum of Montgomery products x*y (each < p^2 < 2^510) in 17 limbs, so 2^34
 // products can be accumulated before overflow.  One Montgomery reduction at the end turns the whole sum into a field

@@ -112,6 +112,23 @@ inline F inverse(const F& a) {  // a^(p-2)
     return acc;
 }
 
+// V * 2^-256 mod p for an unreduced 17-limb (32-bit) integer V = V0 + V1 * 2^256 + v16 * 2^512 — the sum of plain 256x256-bit
+// products of Montgomery-form operands that the resident kernel delivers (kernels.cuh block_sum_wide); the device's
+// fr::wide_reduce computes the same field element.  V0 * R^-1 = mul(V0, 1), V1 * 2^256 * R^-1 = V1, v16 * 2^512 * R^-1 = mul(v16, R^2).
+inline F reduce_wide17(const uint32_t* v) {
+    F v0, v1, top = {{v[16], 0, 0, 0}};
+    for (int i = 0; i < 4; i++) {
+        v0.l[i] = (uint64_t)v[2 * i] | ((uint64_t)v[2 * i + 1] << 32);
+        v1.l[i] = (uint64_t)v[8 + 2 * i] | ((uint64_t)v[8 + 2 * i + 1] << 32);
+    }
+    for (int k = 0; k < 2; k++) {  // 2^256 < 3p
+        if (geq_p(v0.l)) sub_p(v0.l);
+        if (geq_p(v1.l)) sub_p(v1.l);
+    }
+    const F one_int = {{1, 0, 0, 0}};
+    return add(add(mul(v0, one_int), v1), mul(top, R2));
+}
+
 // Lagrange weights w_j = 1 / prod_{k != j} (j - k) for the nodes 0..d (cached per degree; d <= 32)
 inline const std::vector<F>& lagrange_weights(uint32_t d) {
     static std::vector<F> cache[33];

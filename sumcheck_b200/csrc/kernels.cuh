@@ -171,7 +171,7 @@ __device__ __forceinline__ void prepare_fold_consts(const Fr& r, uint32_t* foldC
 // One multiplicand's pair (v0, v1) = (table[2b], table[2b+1]) of product k enters the running product terms of all
 // evaluation points (prover.rs:116-128).  first/last: position of the multiplicand inside its product; kdeg: how many
 // multiplicands the running product holds once this one is in.
-template <int NPTS>
+template <int NPTS, bool ILP = false>
 __device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, bool first, bool last, uint32_t kdeg, const Fr& v0,
                                              const Fr& v1, Fr (&prod)[NPTS], fr::WideAcc (&accw)[NPTS]) {
     // prover.rs:119-124: start = table[2b], step = table[2b+1] - start; product[t] *= start; start += step
@@ -207,6 +207,18 @@ __device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, b
             fr::wide_mac(accw[t], prod[t], cur);
             SC_NEXT_POINT(t)
         }
+    } else if (ILP && p.skip1) {
+        // latency-bound callers: the NPTS points of this multiplicand in ONE out-of-line call (interleaved carry chains)
+        fr::FrN<NPTS> a, b;
+#pragma unroll
+        for (int t = 0; t < NPTS; t++) {
+            a.v[t] = prod[t];
+            b.v[t] = cur;
+            SC_NEXT_POINT(t)
+        }
+        const fr::FrN<NPTS> r = fr::mul_lazy_n<NPTS>(a, b);
+#pragma unroll
+        for (int t = 0; t < NPTS; t++) prod[t] = r.v[t];
     } else {
         // After k multiplicands prod[.] is a degree-k polynomial in the evaluation point, so on consecutive
         // points only k+1 values need a multiply; the others follow by finite differences (integer
@@ -239,7 +251,7 @@ __device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, b
 #undef SC_NEXT_POINT
 }
 
-template <int NPTS, bool FOLD, bool STREAM>
+template <int NPTS, bool FOLD, bool STREAM, bool ILP = false>
 __device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const uint32_t* foldC, unsigned long long b0,
                                                  unsigned long long stride, fr::WideAcc (&accw)[NPTS]) {
     for (unsigned long long b = b0; b < p.n_pairs; b += stride) {
@@ -258,8 +270,14 @@ __device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const uin
                     } else {
                         e0 = load_cg(src); e1 = load_cg(src + 8); e2 = load_cg(src + 16); e3 = load_cg(src + 24);
                     }
-                    v0 = fr::add(e0, FR_MUL_ROUND_CONST(foldC, fr::sub(e1, e0)));
-                    v1 = fr::add(e2, FR_MUL_ROUND_CONST(foldC, fr::sub(e3, e2)));
+                    if (ILP) {
+                        const fr::Fr2 f = fr::mul_round_const_x2(foldC, fr::sub(e1, e0), fr::sub(e3, e2));
+                        v0 = fr::add(e0, f.a);
+                        v1 = fr::add(e2, f.b);
+                    } else {
+                        v0 = fr::add(e0, FR_MUL_ROUND_CONST(foldC, fr::sub(e1, e0)));
+                        v1 = fr::add(e2, FR_MUL_ROUND_CONST(foldC, fr::sub(e3, e2)));
+                    }
                     if (p.write_fold && p.prod_first[jj]) {
                         uint32_t* dst = p.tab_out[idx] + b * 16;
                         fr::store(dst, v0);
@@ -270,9 +288,149 @@ __device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const uin
                     v0 = fr::load_stream(src);
                     v1 = fr::load_stream(src + 8);
                 }
-                consume_pair<NPTS>(p, k, jj == j0, jj + 1 == j1, jj - j0 + 1, v0, v1, prod, accw);
+                consume_pair<NPTS, ILP>(p, k, jj == j0, jj + 1 == j1, jj - j0 + 1, v0, v1, prod, accw);
             }
         }
+    }
+}
+
+// ---- fine-grained pairs (resident rounds with few pairs) ------------------------------------------------------------------------
+// With one pair per thread a latency-bound round still walks ~3500 instructions per warp (6 folds, 6 multiplies, 3 lazy
+// multiply-accumulates at degree 3) on one scheduler.  Here a pair is spread over LPP = 2^lpp_log2 lanes of a warp:
+//   phase A  lane u < 2*nnz folds ONE element: CSR entry u/2 of the product list, half u%2 (new[2b] or new[2b+1]), stores it
+//            (first use of the table) and parks it in the warp's shared-memory slots;
+//   phase B  lane u < n_products*NPTS owns (product u/NPTS, evaluation point u%NPTS): it builds that point of every
+//            multiplicand from the parked pair (prover.rs:119-124) and runs the product chain into ITS lazy accumulator.
+// ~1000 instructions per lane instead of ~3500.  Needs 2*nnz <= 32 and n_products*NPTS <= 32; exact arithmetic, same limbs.
+// slots: this warp's [32][8] words.  b = the pair this lane group works on (b >= p.n_pairs: idle).  On return `acc` holds the
+// lane's contribution and `my_pt` its point slot (or -1).
+template <int NPTS>
+__device__ __forceinline__ void accumulate_fine(const RoundParams& p, const uint32_t* foldC, uint32_t* slots, unsigned long long b,
+                                                uint32_t lpp_log2, fr::WideAcc& acc, int& my_pt) {
+    const uint32_t lane = threadIdx.x & 31, lpp = 1u << lpp_log2, u = lane & (lpp - 1), base = lane - u;
+    const uint32_t nnz = p.prod_offsets[p.n_products];
+    const bool live = b < p.n_pairs;
+    if (live && u < 2 * nnz) {  // phase A
+        const uint32_t jj = u >> 1, h = u & 1u, idx = p.prod_indices[jj];
+        const uint32_t* src = p.tab_in[idx] + b * 32 + h * 16;
+        const Fr e0 = load_cg(src), e1 = load_cg(src + 8);
+        const Fr v = fr::add(e0, FR_MUL_ROUND_CONST(foldC, fr::sub(e1, e0)));
+        if (p.write_fold && p.prod_first[jj]) fr::store(p.tab_out[idx] + b * 16 + h * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; i++) slots[(base + u) * 8 + i] = v.l[i];
+    }
+    __syncwarp();
+    my_pt = -1;
+    fr::wide_zero(acc);
+    if (live && u < p.n_products * NPTS) {  // phase B
+        const uint32_t k = u / NPTS, s = u % NPTS;
+        my_pt = (int)s;
+        const uint32_t steps = p.skip1 ? (s == 0 ? 0u : s + 1u) : p.t0 + s;  // the evaluation point of slot s
+        const uint32_t j0 = p.prod_offsets[k], j1 = p.prod_offsets[k + 1];
+        Fr prod = fr::zero();
+        for (uint32_t jj = j0; jj < j1; jj++) {
+            Fr v0, v1;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                v0.l[i] = slots[(base + 2 * jj) * 8 + i];
+                v1.l[i] = slots[(base + 2 * jj + 1) * 8 + i];
+            }
+            const Fr step = fr::sub(v1, v0);
+            Fr cur = v0;
+            for (uint32_t a = 0; a < steps; a++) cur = fr::add(cur, step);
+            const bool first = jj == j0, last = jj + 1 == j1;
+            if (first && !p.defer_coeff && !(p.prod_scaled && p.prod_scaled[k])) cur = fr::mul(cur, fr::load(p.coeffs + 8 * k));
+            if (first && last) fr::wide_add_shifted(acc, cur);
+            else if (first) prod = cur;
+            else if (last) fr::wide_mac(acc, prod, cur);
+            else prod = fr::mul_lazy(prod, cur);
+        }
+    }
+}
+
+// ---- integer block sum of lazily reduced accumulators (resident rounds) ------------------------------------------------------
+// The per-thread sums of a round are UNREDUCED 17-limb integers (fr::WideAcc).  Instead of Montgomery-reducing every thread's
+// sums and adding field elements through a shuffle tree (wide_reduce + block_reduce: ~5300 cycles of dependent latency for
+// three points), the limbs are added as plain integers — 16-bit halves through redux.sync, so no carry crosses a lane — and the
+// ONE resulting 17-limb integer per point goes to the host, which reduces it (host_fr.h; ~0.1 us of CPU).  A round has fewer
+// than 2^34 products, so the total fits the 17 limbs (each product is below 2^510).
+constexpr int WL = 17;
+
+// per-limb 64-bit sums (tot[t * WL + i], shared or global memory) -> carry-propagated 17-limb integers in s_out; all threads call it
+template <int NPTS, bool GLOBAL = false>
+__device__ __forceinline__ void carry_wide(const unsigned long long* tot, uint32_t* s_out) {
+    if (threadIdx.x < NPTS) {
+        unsigned long long c = 0;
+#pragma unroll
+        for (int i = 0; i < WL; i++) {
+            c += GLOBAL ? __ldcg(tot + threadIdx.x * WL + i) : tot[threadIdx.x * WL + i];
+            s_out[threadIdx.x * WL + i] = (uint32_t)c;
+            c >>= 32;
+        }
+    }
+    __syncthreads();
+}
+
+// All threads call it.  s_part: [nwarps][NPTS * WL] u64, s_tot: [NPTS * WL] u64, s_out: [NPTS * WL] u32 (the result).
+template <int NPTS>
+__device__ __forceinline__ void block_sum_wide(const fr::WideAcc (&a)[NPTS], unsigned long long* s_part, unsigned long long* s_tot, uint32_t* s_out,
+                                               bool carry = true) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int t = 0; t < NPTS; t++) {
+#pragma unroll
+        for (int i = 0; i < WL; i++) {
+            const uint32_t lo = __reduce_add_sync(0xffffffffu, a[t].l[i] & 0xffffu);
+            const uint32_t hi = __reduce_add_sync(0xffffffffu, a[t].l[i] >> 16);
+            if (lane == 0) s_part[(size_t)warp * NPTS * WL + t * WL + i] = (unsigned long long)lo + ((unsigned long long)hi << 16);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NPTS * WL) {
+        unsigned long long tot = 0;
+        for (int w = 0; w < nwarps; w++) tot += s_part[(size_t)w * NPTS * WL + threadIdx.x];
+        s_tot[threadIdx.x] = tot;
+    }
+    __syncthreads();
+    if (!carry) return;  // the caller adds s_tot (per-limb sums, no carries yet) into the grid's totals
+    carry_wide<NPTS>(s_tot, s_out);
+}
+
+// The same for ONE accumulator per thread that belongs to point `my_pt` (accumulate_fine): the other points see zeros.
+template <int NPTS>
+__device__ __forceinline__ void block_sum_wide_sel(const fr::WideAcc& a, int my_pt, unsigned long long* s_part, unsigned long long* s_tot,
+                                                   uint32_t* s_out, bool carry = true) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int t = 0; t < NPTS; t++) {
+        const uint32_t m = (my_pt == t) ? 0xffffffffu : 0u;
+#pragma unroll
+        for (int i = 0; i < WL; i++) {
+            const uint32_t v = a.l[i] & m;
+            const uint32_t lo = __reduce_add_sync(0xffffffffu, v & 0xffffu);
+            const uint32_t hi = __reduce_add_sync(0xffffffffu, v >> 16);
+            if (lane == 0) s_part[(size_t)warp * NPTS * WL + t * WL + i] = (unsigned long long)lo + ((unsigned long long)hi << 16);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NPTS * WL) {
+        unsigned long long tot = 0;
+        for (int w = 0; w < nwarps; w++) tot += s_part[(size_t)w * NPTS * WL + threadIdx.x];
+        s_tot[threadIdx.x] = tot;
+    }
+    __syncthreads();
+    if (!carry) return;  // the caller adds s_tot (per-limb sums, no carries yet) into the grid's totals
+    carry_wide<NPTS>(s_tot, s_out);
+}
+
+// w += the 17-limb integer at src (last-arrival sum of the per-CTA partials; not a hot path)
+__device__ __forceinline__ void wide_add_limbs(fr::WideAcc& w, const uint32_t* src) {
+    unsigned long long c = 0;
+#pragma unroll
+    for (int i = 0; i < WL; i++) {
+        c += (unsigned long long)w.l[i] + src[i];
+        w.l[i] = (uint32_t)c;
+        c >>= 32;
     }
 }
 
@@ -345,7 +503,7 @@ __device__ __forceinline__ void publish_round(const RoundParams& p, const Fr (&a
 #define SC_THREADS 128
 #endif
 constexpr int ROUND_THREADS = SC_THREADS;  // CTA size of round_kernel in this translation unit
-constexpr uint32_t MAIL_WORDS = 128;  // per (slot, rank): up to 6 points x 8 limbs, each as a {limb, sequence number} pair
+constexpr uint32_t MAIL_WORDS = 256;  // per (slot, rank): up to 128 {value, sequence number} pairs — 6 points x 8 limbs, or 5 x 17 limbs of unreduced sums
 constexpr uint32_t MAIL_SLOTS = 64;
 
 // One mailbox word = {limb, sequence number} packed into ONE 64-bit register and moved with a scalar 8-byte access.  The
@@ -420,6 +578,46 @@ __device__ __forceinline__ void exchange_partials(const RoundParams& p, Fr (&acc
                 s = fr::add(s, x);
             }
             acc[t] = s;
+        }
+    }
+    __syncwarp();
+}
+
+// The same exchange for UNREDUCED sums (resident rounds): s_vals holds this rank's NPTS * WL limbs; on return it holds the
+// integer sums over all ranks (they fit the 17 limbs, see block_sum_wide).  Executed by warp 0.  s_rows: [G][NPTS * WL].
+template <int NPTS>
+__device__ __forceinline__ void exchange_wide(const RoundParams& p, uint32_t* s_vals, uint32_t* s_rows) {
+    const uint32_t lane = threadIdx.x & 31, G = p.n_ranks;
+    constexpr uint32_t NW = NPTS * WL;
+    for (uint32_t w = lane; w < NW; w += 32) {
+        const uint32_t v = s_vals[w];
+        for (uint32_t g = 0; g < G; g++)
+            mail_store(p.peer_mail[g] + ((size_t)p.mail_slot * G + p.rank) * MAIL_WORDS + 2 * w, v, p.mail_seq);
+    }
+    const uint32_t* mine = p.peer_mail[p.rank] + (size_t)p.mail_slot * G * MAIL_WORDS;
+    for (uint32_t w = lane; w < NW; w += 32) {
+        for (uint32_t g = 0; g < G; g++) {
+            uint32_t d, f;
+            const long long t0 = clock64();
+            for (;;) {
+                mail_load(mine + (size_t)g * MAIL_WORDS + 2 * w, d, f);
+                if (f == p.mail_seq) break;
+                if (clock64() - t0 > p.mail_timeout) {
+                    *p.comm_error = 1;
+                    d = 0;
+                    break;
+                }
+            }
+            s_rows[g * NW + w] = d;
+        }
+    }
+    __syncwarp();
+    if (lane < (uint32_t)NPTS) {
+        unsigned long long c = 0;
+        for (int i = 0; i < WL; i++) {
+            for (uint32_t g = 0; g < G; g++) c += s_rows[g * NW + lane * WL + i];
+            s_vals[lane * WL + i] = (uint32_t)c;
+            c >>= 32;
         }
     }
     __syncwarp();

@@ -8,11 +8,13 @@
 //   host  -> device   the round's fold constants C[k] = r * 2^(32k+64) mod p (fr.cuh fold_const; 64 limbs), computed by
 //                     the host from the challenge it has just drawn; CTA 0 polls them over PCIe and re-publishes them in
 //                     device memory for the other CTAs
-//   device -> host    the round's raw sums P(0), P(2), .., P(d) (kernels.cuh RoundParams::raw_out semantics); the host
+//   device -> host    the round's sums for P(0), P(2), .., P(d) as UNREDUCED 17-limb integers (the lazily accumulated products,
+//                     added limb-wise over the threads: kernels.cuh block_sum_wide); the host Montgomery-reduces them and
 //                     finishes the message (deferred coefficient, P(1) from the claim, canonical forms — host_fr.h)
 //
 // Per round every active CTA folds + sums its pairs (accumulate_pairs, the same arithmetic as round_kernel<NPTS, true>),
-// the last CTA to arrive adds the per-CTA partials and publishes.  A round's tables are written by other CTAs of the same
+// the last CTA to arrive adds the per-CTA sums and publishes.  Inside a pair the two folds of a table and the d points of
+// a multiplicand go through ILP-interleaved out-of-line routines (fr.cuh mul_round_const_x2, mul_lazy_n).  A round's tables are written by other CTAs of the same
 // launch, so they are read with ld.global.cg (L2) and every thread fences its stores before the block's arrival.
 // No grid-wide barrier is needed: a CTA proceeds to round k+1 only when it sees that round's constants, and the host
 // sends those only after the LAST arrival of round k — every store of round k happens-before every load of round k+1.
@@ -25,19 +27,43 @@ namespace sck {
 
 template <int NPTS>
 __global__ void __launch_bounds__(RES_THREADS, 2) resident_kernel(const ResidentParams q) {
-    __shared__ uint32_t s_red[32 * NPTS * 8];
+    constexpr int NW = NPTS * WL;
+    __shared__ unsigned long long s_part[(RES_THREADS / 32) * NW], s_tot[NW];
+    __shared__ uint32_t s_out[NW];
+    __shared__ uint32_t s_rows[16 * NW];  // sharded: the ranks' sums (n_ranks <= 16)
     __shared__ __align__(16) uint32_t s_foldC[RES_CONST_WORDS];
+    __shared__ uint32_t s_slots[(RES_THREADS / 32) * 32 * 8];  // fine-grained rounds: one folded element per lane
     __shared__ volatile int s_flag;
     const uint32_t tid = threadIdx.x, c = blockIdx.x;
+    // CTAs a round needs: RES_THREADS pairs per CTA, or (fine-grained) RES_THREADS >> lpp_log2
+    auto ctas_for = [&](uint32_t rd, bool& fine) {
+        const unsigned long long n = q.n_pairs_first >> rd;
+        fine = q.fine_max_pairs && n <= q.fine_max_pairs;
+        const unsigned long long per = fine ? (unsigned long long)(RES_THREADS >> q.lpp_log2) : (unsigned long long)RES_THREADS;
+        const unsigned long long want = (n + per - 1) / per;
+        return want < (unsigned long long)gridDim.x ? (want ? (uint32_t)want : 1u) : gridDim.x;
+    };
     RoundParams p = q.rp;
     int cur = q.cur;
     if (tid == 0) s_flag = 0;
     __syncthreads();
     for (uint32_t rd = 0; rd < q.n_rounds; rd++) {
         const unsigned long long n_pairs = q.n_pairs_first >> rd;
-        const unsigned long long want = (n_pairs + RES_THREADS - 1) / RES_THREADS;
-        const uint32_t n_act = want < (unsigned long long)gridDim.x ? (want ? (uint32_t)want : 1u) : gridDim.x;
-        if (c >= n_act) return;  // this CTA has no pairs in this round, nor in any later one
+        bool fine;
+        const uint32_t n_act = ctas_for(rd, fine);
+        if (c >= n_act) {
+            // no pairs for this CTA in this round; the fine-grained rounds that follow may need it again (they use more CTAs
+            // per pair), otherwise it leaves for good
+            uint32_t later = 0;
+            for (uint32_t r2 = rd + 1; r2 < q.n_rounds; r2++) {
+                bool f2;
+                const uint32_t a2 = ctas_for(r2, f2);
+                later = a2 > later ? a2 : later;
+            }
+            if (c >= later) return;
+            cur = (cur == 1) ? 2 : 1;
+            continue;
+        }
         const uint32_t seq = q.seq0 + rd;
         const long long tk0 = clock64();
         // ---- this round's fold constants: CTA 0 from the host (PCIe reads), the others from CTA 0's copy in device memory
@@ -46,11 +72,7 @@ __global__ void __launch_bounds__(RES_THREADS, 2) resident_kernel(const Resident
             uint32_t v = 0, f = 0;
             const long long t0 = clock64();
             for (;;) {
-                if (q.flags & 2u) {
-                    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(src) : "memory");
-                } else {
-                    mail_load(src, v, f);
-                }
+                mail_load(src, v, f);
                 if (f == seq) break;
                 if (tid == 0) {  // the host abandoned the proof (an error path): leave at once, and tell the other CTAs
                     uint32_t a;
@@ -84,67 +106,71 @@ __global__ void __launch_bounds__(RES_THREADS, 2) resident_kernel(const Resident
         p.tab_out = q.ptrs[nxt];
         p.n_pairs = n_pairs;
         fr::WideAcc accw[NPTS];
+        long long tk2;
+        if (fine) {
+            // several lanes per pair; a CTA covers RES_THREADS >> lpp_log2 pairs per sweep
+            const uint32_t per_warp = 32u >> q.lpp_log2, per_cta = (RES_THREADS / 32) * per_warp;
+            fr::WideAcc mine, part;
+            fr::wide_zero(mine);
+            int my_pt = -1;
+            for (unsigned long long b0 = (unsigned long long)c * per_cta; b0 < n_pairs; b0 += (unsigned long long)n_act * per_cta) {
+                int pt;
+                accumulate_fine<NPTS>(p, s_foldC, s_slots + (tid >> 5) * 32 * 8, b0 + (tid >> 5) * per_warp + ((tid & 31) >> q.lpp_log2), q.lpp_log2,
+                                      part, pt);
+                if (pt >= 0) {
+                    my_pt = pt;
+                    wide_add_limbs(mine, part.l);
+                }
+                __syncwarp();
+            }
+            __threadfence();
+            tk2 = clock64();
+            block_sum_wide_sel<NPTS>(mine, my_pt, s_part, s_tot, s_out, n_act == 1);
+        } else {
 #pragma unroll
-        for (int t = 0; t < NPTS; t++) fr::wide_zero(accw[t]);
-        accumulate_pairs<NPTS, true, false>(p, s_foldC, (unsigned long long)c * RES_THREADS + tid, (unsigned long long)n_act * RES_THREADS, accw);
-        __threadfence();  // this thread's folded-table stores are visible GPU-wide before the CTA reports its arrival
-        const long long tk2 = clock64();
-        Fr acc[NPTS];
-#pragma unroll
-        for (int t = 0; t < NPTS; t++) acc[t] = fr::wide_reduce(accw[t]);
-        block_reduce<NPTS>(acc, s_red);
+            for (int t = 0; t < NPTS; t++) fr::wide_zero(accw[t]);
+            accumulate_pairs<NPTS, true, false, true>(p, s_foldC, (unsigned long long)c * RES_THREADS + tid, (unsigned long long)n_act * RES_THREADS, accw);
+            __threadfence();  // this thread's folded-table stores are visible GPU-wide before the CTA reports its arrival
+            tk2 = clock64();
+            block_sum_wide<NPTS>(accw, s_part, s_tot, s_out, n_act == 1);  // the CTA's sums as NPTS 17-limb integers (no Montgomery reduction)
+        }
         bool publisher = true;
         if (n_act > 1) {
-            uint32_t* part = q.partials + (size_t)(rd & 1u) * gridDim.x * NPTS * 8;
-            if (tid == 0) {
-#pragma unroll
-                for (int t = 0; t < NPTS; t++) fr::store(part + ((size_t)c * NPTS + t) * 8, acc[t]);
+            // several CTAs: every CTA adds its per-limb sums into the grid's totals with 64-bit reductions (no carries yet: a
+            // limb sum stays below 2^48), the last CTA to arrive carries them out and clears the totals for their next use
+            unsigned long long* tot = q.totals + (size_t)(rd & 1u) * NW;
+            if (tid < NW) {
+                atomicAdd(tot + tid, s_tot[tid]);
                 __threadfence();
+            }
+            __syncthreads();
+            if (tid == 0) {
                 const unsigned int ticket = atomicAdd(q.counters + rd, 1u);
                 s_flag = (ticket == n_act - 1) ? 1 : 0;
             }
             __syncthreads();
             publisher = s_flag == 1;
-            if (publisher) {  // last arrival: add the per-CTA partials (prover.rs:138-148, the rayon reduce)
+            if (publisher) {
                 __threadfence();
-#pragma unroll
-                for (int t = 0; t < NPTS; t++) acc[t] = fr::zero();
-                for (uint32_t g = tid; g < n_act; g += RES_THREADS) {
-#pragma unroll
-                    for (int t = 0; t < NPTS; t++) acc[t] = fr::add(acc[t], load_cg(part + ((size_t)g * NPTS + t) * 8));
-                }
-                block_reduce<NPTS>(acc, s_red);
+                carry_wide<NPTS, true>(tot, s_out);
+                if (tid < NW) tot[tid] = 0;  // this buffer serves round rd + 2 next; its CTAs start after this round is published
             }
         }
         const long long tk3 = clock64();
         if (publisher && tid < 32) {
-            if (p.peer_mail) {  // sharded: all-to-all of the partial sums over NVLink peer memory, then the global sums
+            if (p.peer_mail) {  // sharded: all-to-all of the unreduced sums over NVLink peer memory, then the global sums
                 p.mail_seq = q.mail_seq0 + rd;
                 p.mail_slot = p.mail_seq % MAIL_SLOTS;
-                exchange_partials<NPTS>(p, acc, s_red);
+                exchange_wide<NPTS>(p, s_out, s_rows);
             }
-            if (tid == 0) {
-#pragma unroll
-                for (int t = 0; t < NPTS; t++)
-#pragma unroll
-                    for (int i = 0; i < 8; i++) s_red[t * 8 + i] = acc[t].l[i];
-            }
-            __syncwarp();
             // one 8-byte {limb, seq} store per limb straight into mapped host memory: no fence, no separate flag
-            for (uint32_t w = tid; w < (uint32_t)NPTS * 8; w += 32) {
-                if (q.flags & 2u) {
-                    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(q.h_sums + 2 * w), "r"(s_red[w]), "r"(seq) : "memory");
-                } else {
-                    mail_store(q.h_sums + 2 * w, s_red[w], seq);
-                }
-            }
-            if (q.flags & 1u) __threadfence_system();
+            for (uint32_t w = tid; w < (uint32_t)NW; w += 32) mail_store(q.h_sums + 2 * w, s_out[w], seq);
         }
         if (q.prof && c == 0 && tid == 0) {
             const long long tk4 = clock64();
             q.prof[rd * 4 + 0] = tk1 - tk0; q.prof[rd * 4 + 1] = tk2 - tk1; q.prof[rd * 4 + 2] = tk3 - tk2; q.prof[rd * 4 + 3] = tk4 - tk3;
         }
-        __syncthreads();  // s_red / s_foldC / s_flag are reused by the next round
+        __syncthreads();  // the shared arrays and s_flag are reused by the next round
         cur = nxt;
     }
 }

@@ -119,7 +119,7 @@ struct AllocCache {
 AllocCache g_cache[64];
 std::mutex g_cache_mu;
 // resident rounds: host <-> device words (see resident_kernel.cuh); byte offsets inside the mapped block
-constexpr size_t RES_OFF_CONSTS = 0, RES_OFF_SUMS = 512, RES_OFF_ERROR = 1024, RES_OFF_ABORT = 1088, RES_HOST_BYTES = 1280;
+constexpr size_t RES_OFF_CONSTS = 0, RES_OFF_SUMS = 512, RES_OFF_ERROR = 1536, RES_OFF_ABORT = 1600, RES_HOST_BYTES = 1792;
 constexpr size_t RES_BCAST_BYTES = 64 * 8 + 64;
 constexpr unsigned long long RES_MAX_PAIRS_DEFAULT = 1ull << 16;
 constexpr uint32_t EAGER_CHUNKS = 8;
@@ -295,6 +295,7 @@ struct sc_prover {
     std::vector<int> scaled_table;
     uint8_t* d_scaled = nullptr;
     std::vector<uint32_t> h_offsets, h_indices;
+    size_t h_nnz = 0;                  // offsets[n_products]
     std::vector<uint64_t> h_lagrange;  // staging copy of d_lagrange (uploaded asynchronously)
     // Resident rounds (resident_kernel.cuh): set by run_rounds for the proof in flight
     uint32_t res_first = 0;            // first (1-based) round served by the resident kernel; 0 = none
@@ -568,6 +569,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     // Two allocations for everything else (creation cost matters for one-shot proofs and the two GKR phases):
     // one device slab = ping-pong tables + all small arrays, one pinned+mapped host block.
     const uint32_t nnz = offsets[n_products];
+    p->h_nnz = nnz;
     p->max_grid = g_dev[device].sms * 32;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off = 0;
@@ -916,13 +918,23 @@ int resident_launch(sc_prover* p) {
     q.h_abort = (const uint32_t*)((uint8_t*)p->d_res + RES_OFF_ABORT);
     q.d_bcast = p->d_res_bcast;
     q.d_abort = p->d_res_bcast + 128;
-    q.partials = p->d_partials;
+    q.totals = (unsigned long long*)p->d_partials;  // [2][NPTS][17] u64
     q.counters = p->d_res_counters;
+    CUDA_TRY(cudaMemsetAsync(p->d_partials, 0, 2 * sck::MAX_NPTS * 17 * sizeof(unsigned long long), p->stream));
+    {   // fine-grained rounds: every pair spread over 2^lpp lanes (kernels.cuh accumulate_fine)
+        const uint32_t nnz = (uint32_t)p->h_nnz, units = 2 * nnz > p->n_products * d ? 2 * nnz : p->n_products * d;
+        if (units <= 32 && !getenv("SC_RES_NO_FINE")) {
+            uint32_t lg = 0;
+            while ((1u << lg) < units) lg++;
+            q.lpp_log2 = lg;
+            const char* e = getenv("SC_RES_FINE_MAX_PAIRS");
+            q.fine_max_pairs = e ? strtoull(e, nullptr, 10) : 2048;
+        }
+    }
     const int khz = g_dev[p->device].khz;
     static const double secs = getenv("SC_RES_TIMEOUT_S") ? atof(getenv("SC_RES_TIMEOUT_S")) : 10.0;
     q.timeout = (long long)(secs * (khz > 0 ? khz : 1965000) * 1000.0);
     *(volatile uint32_t*)((uint8_t*)p->h_res + RES_OFF_ERROR) = 0;
-    if (const char* f = getenv("SC_RES_FLAGS")) q.flags = (uint32_t)atoi(f);
     if (getenv("SC_RES_PROF")) {
         if (!p->d_res_prof) CUDA_TRY(cudaMalloc(&p->d_res_prof, 64 * 4 * sizeof(long long)));
         CUDA_TRY(cudaMemsetAsync(p->d_res_prof, 0, 64 * 4 * sizeof(long long), p->stream));
@@ -930,15 +942,18 @@ int resident_launch(sc_prover* p) {
     }
     CUDA_TRY(cudaMemsetAsync(p->d_res_counters, 0, 64 * sizeof(unsigned int), p->stream));
     unsigned long long need = (q.n_pairs_first + sck::RES_THREADS - 1) / sck::RES_THREADS;
+    for (uint32_t rd = 0; rd < q.n_rounds && q.fine_max_pairs; rd++) {  // the fine-grained rounds use more CTAs per pair
+        const unsigned long long n = q.n_pairs_first >> rd, per = sck::RES_THREADS >> q.lpp_log2;
+        if (n <= q.fine_max_pairs && (n + per - 1) / per > need) need = (n + per - 1) / per;
+    }
     unsigned long long cap = (unsigned long long)sck::resident_max_grid(d, p->device, g_dev[p->device].sms);
-    if (cap * 2 > (unsigned long long)p->max_grid) cap = p->max_grid / 2;  // partials: [2][grid][NPTS][8]
     // ranks sharing a device (sc_prover_create_multi with a repeated device id): their resident kernels wait for each other's
     // partial sums, so ALL of them must fit on the device at once — next to the launch-per-round kernels of a rank that is
     // still a round behind (half of the device is left to those)
     if (comm_device_share(p) > 1) cap /= 2ull * (unsigned long long)comm_device_share(p);
     if (cap < 1) cap = 1;
     const int grid = (int)(need < cap ? (need ? need : 1) : cap);
-    cudaError_t e = sck::launch_resident(d, grid, q, p->stream);
+    cudaError_t e = sck::launch_resident(d, grid, q, p->stream, comm_device_share(p) == 1);
     if (e != cudaSuccess) return fail(SC_ERR_CUDA, "resident kernel launch: %s", cudaGetErrorString(e));
     p->launches++;
     p->res_running = true;
@@ -984,9 +999,10 @@ int resident_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
         }
     }
     const double h1 = prof ? now_us() : 0;
-    // wait for the d raw sums: every limb arrives as one {limb, seq} word
+    // wait for the d sums: unreduced 17-limb integers, every limb one {limb, seq} word
     const uint64_t* hs = (const uint64_t*)((uint8_t*)w->h_res + RES_OFF_SUMS);
-    const uint32_t n_words = d * 8;
+    const uint32_t n_words = d * 17;
+    uint32_t wide[sck::MAX_NPTS * 17];
     SpinWait sw;
     for (uint32_t k = 0; k < n_words; k++) {
         uint64_t v;
@@ -1005,10 +1021,14 @@ int resident_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
                 }
             }
         }
-        w->h_result[k] = (uint32_t)v;
+        wide[k] = (uint32_t)v;
     }
     __sync_synchronize();
     const double h2 = prof ? now_us() : 0;
+    for (uint32_t t = 0; t < d; t++) {  // V * R^-1 mod p: what fr::wide_reduce computes on the device
+        const hfr::F s = hfr::reduce_wide17(wide + 17 * t);
+        memcpy(w->h_result + (size_t)t * 8, &s, 32);
+    }
     w->raw_npts = d;
     w->used_skip1 = true;
     host_finish_round(p, w, r);

@@ -136,7 +136,7 @@ int resident_max_grid(uint32_t npts, int device, int sms) {
     return v * sms;
 }
 
-cudaError_t launch_resident(uint32_t npts, int grid, const ResidentParams& rp, cudaStream_t stream) {
+cudaError_t launch_resident(uint32_t npts, int grid, const ResidentParams& rp, cudaStream_t stream, bool cooperative) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(RES_THREADS);
@@ -146,7 +146,7 @@ cudaError_t launch_resident(uint32_t npts, int grid, const ResidentParams& rp, c
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = getenv("SC_RES_NO_COOP") ? 0 : 1;  // measured: no difference in launch cost; cooperative guarantees co-residency
+    cfg.numAttrs = (cooperative && !getenv("SC_RES_NO_COOP")) ? 1 : 0;  // measured: no difference in launch cost; cooperative guarantees co-residency
     switch (npts) {
         case 1: return cudaLaunchKernelEx(&cfg, resident_kernel<1>, rp);
         case 2: return cudaLaunchKernelEx(&cfg, resident_kernel<2>, rp);

@@ -33,21 +33,26 @@ struct ResidentParams {
     uint32_t seq0;                     // sequence number of the first resident round; +1 per round
     uint32_t mail_seq0;                // sharded: mailbox sequence number of the first resident round
     const uint32_t* h_consts;          // mapped host memory: [64] {limb, seq}
-    uint32_t* h_sums;                  // mapped host memory: [NPTS * 8] {limb, seq}
+    uint32_t* h_sums;                  // mapped host memory: [NPTS * 17] {limb, seq}: unreduced sums
     uint32_t* h_error;                 // mapped host word: set to 1 when the host (or a peer) did not answer in time
     const uint32_t* h_abort;           // mapped host word: the host sets it to seq0 when it abandons the proof (error paths)
     uint32_t* d_abort;                 // device word through which CTA 0 passes the abort on
     uint32_t* d_bcast;                 // device memory: [64] {limb, seq}, CTA 0 -> the other CTAs
-    uint32_t* partials;                // device memory: [2][gridDim.x][NPTS][8]
+    unsigned long long* totals;        // device memory: [2][NPTS][17] per-limb sums over the CTAs of a round, zeroed before the launch
     unsigned int* counters;            // device memory: [n_rounds], zeroed before the launch
+    // fine-grained rounds (kernels.cuh accumulate_fine): rounds with at most fine_max_pairs pairs spread every pair over
+    // 2^lpp_log2 lanes; 0 = never
+    unsigned long long fine_max_pairs;
+    uint32_t lpp_log2;
     long long timeout;                 // clock64 ticks to wait for the host
-    uint32_t flags;                    // experiments (SC_RES_FLAGS): 1 = system fence after publishing, 2 = volatile accesses
     long long* prof;                   // optional [n_rounds][4] cycle counts of CTA 0: wait, accumulate, reduce, publish (SC_RES_PROF)
 };
 
 cudaError_t tail_init_constants();
 int resident_max_grid(uint32_t npts, int device, int sms);  // co-resident CTAs of resident_kernel<npts> (cooperative launch)
-cudaError_t launch_resident(uint32_t npts, int grid, const ResidentParams& rp, cudaStream_t stream);
+// cooperative = false for ranks that share a device: two cooperative grids that wait for each other's partial sums must not be
+// serialised by the launch mechanism; their co-residency then follows from the grid cap alone (resident_launch)
+cudaError_t launch_resident(uint32_t npts, int grid, const ResidentParams& rp, cudaStream_t stream, bool cooperative);
 int fold_round_occupancy(uint32_t npts);
 int fold_round_threads();
 cudaError_t launch_fold_round(uint32_t npts, int grid, const RoundParams& rp, cudaStream_t stream);

@@ -33,7 +33,17 @@ def _instance(orc, nv, n_products, m, seed):
     return tabs, prods
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+# at most 4 ranks share one device here (8 ranks on ONE GPU oversubscribe it with spinning last blocks; the 8-rank case runs
+# where there are at least 2 devices)
+@pytest.mark.parametrize("world", [w for w in (2, 4, 8) if w <= 4 * max(_n_gpus(), 1)])
 def test_single_process_sharded_prover_matches_oracle(orc, world):
     import sumcheck_b200 as sc
     devs = _devices(world)
@@ -134,14 +144,6 @@ def _worker(rank, world, port, q):
         q.put((rank, results))
     finally:
         dist.destroy_process_group()
-
-
-def _n_gpus():
-    try:
-        import torch
-        return torch.cuda.device_count()
-    except Exception:
-        return 0
 
 
 # One process per GPU needs as many devices as ranks (NCCL refuses two ranks on one device); the world sizes this box cannot
