@@ -171,9 +171,19 @@ __device__ __forceinline__ void prepare_fold_consts(const Fr& r, uint32_t* foldC
 // One multiplicand's pair (v0, v1) = (table[2b], table[2b+1]) of product k enters the running product terms of all
 // evaluation points (prover.rs:116-128).  first/last: position of the multiplicand inside its product; kdeg: how many
 // multiplicands the running product holds once this one is in.
-template <int NPTS, bool ILP = false>
-__device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, bool first, bool last, uint32_t kdeg, const Fr& v0,
-                                             const Fr& v1, Fr (&prod)[NPTS], fr::WideAcc (&accw)[NPTS]) {
+// Where the lazily reduced sums of a thread live: in registers (17 limbs per evaluation point) ...
+template <int NPTS>
+struct RegAccs {
+    fr::WideAcc (&a)[NPTS];
+    __device__ __forceinline__ void mac(int t, const Fr& x, const Fr& y) { fr::wide_mac(a[t], x, y); }
+    __device__ __forceinline__ void add_shifted(int t, const Fr& x) { fr::wide_add_shifted(a[t], x); }
+    __device__ __forceinline__ void begin() {}
+};
+// ... or parked in tensor memory (tma_round1.cuh TmemAccs): same interface.
+
+template <int NPTS, bool ILP = false, class ACCS>
+__device__ __forceinline__ void consume_pair_acc(const RoundParams& p, uint32_t k, bool first, bool last, uint32_t kdeg, const Fr& v0,
+                                                 const Fr& v1, Fr (&prod)[NPTS], ACCS& accs) {
     // prover.rs:119-124: start = table[2b], step = table[2b+1] - start; product[t] *= start; start += step
     Fr step = fr::sub(v1, v0);
     Fr cur = v0;
@@ -190,9 +200,10 @@ __device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, b
         if ((t) == 0 && p.skip1) cur = fr::add(cur, step);      \
     }
     if (first && last) {  // single multiplicand: contributes its value itself
+        accs.begin();
 #pragma unroll
         for (int t = 0; t < NPTS; t++) {
-            fr::wide_add_shifted(accw[t], cur);
+            accs.add_shifted(t, cur);
             SC_NEXT_POINT(t)
         }
     } else if (first) {
@@ -202,9 +213,10 @@ __device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, b
             SC_NEXT_POINT(t)
         }
     } else if (last) {  // prover.rs:126-128 fused with the last multiply: products_sum[t] += product[t]*start
+        accs.begin();
 #pragma unroll
         for (int t = 0; t < NPTS; t++) {
-            fr::wide_mac(accw[t], prod[t], cur);
+            accs.mac(t, prod[t], cur);
             SC_NEXT_POINT(t)
         }
     } else if (ILP && p.skip1) {
@@ -249,6 +261,13 @@ __device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, b
         }
     }
 #undef SC_NEXT_POINT
+}
+
+template <int NPTS, bool ILP = false>
+__device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, bool first, bool last, uint32_t kdeg, const Fr& v0,
+                                             const Fr& v1, Fr (&prod)[NPTS], fr::WideAcc (&accw)[NPTS]) {
+    RegAccs<NPTS> accs{accw};
+    consume_pair_acc<NPTS, ILP>(p, k, first, last, kdeg, v0, v1, prod, accs);
 }
 
 template <int NPTS, bool FOLD, bool STREAM, bool ILP = false>
@@ -626,12 +645,20 @@ __device__ __forceinline__ void exchange_wide(const RoundParams& p, uint32_t* s_
 // Everything after the hot loop: per-thread lazy sums -> field elements -> block sum -> (last block) grid sum ->
 // (sharded) exchange with the peer GPUs -> deferred coefficient, P(1) from the claim, publication.
 template <int NPTS>
+__device__ __forceinline__ void finish_round_reduced(const RoundParams& p, Fr (&acc)[NPTS], const Fr& r, uint32_t* s_red, bool* s_last_p);
+
+template <int NPTS>
 __device__ __forceinline__ void finish_round(const RoundParams& p, fr::WideAcc (&accw)[NPTS], const Fr& r, uint32_t* s_red, bool* s_last_p) {
-    bool& s_last = *s_last_p;
     Fr acc[NPTS];
 #pragma unroll
     for (int t = 0; t < NPTS; t++) acc[t] = fr::wide_reduce(accw[t]);
+    finish_round_reduced<NPTS>(p, acc, r, s_red, s_last_p);
+}
 
+// acc[t]: this thread's sums as field elements
+template <int NPTS>
+__device__ __forceinline__ void finish_round_reduced(const RoundParams& p, Fr (&acc)[NPTS], const Fr& r, uint32_t* s_red, bool* s_last_p) {
+    bool& s_last = *s_last_p;
     block_reduce<NPTS>(acc, s_red);
     if (gridDim.x > 1) {  // a single-CTA launch (small rounds) already holds the grand totals in thread 0
         if (threadIdx.x == 0) {

@@ -11,7 +11,7 @@
 namespace sck {
 
 #ifndef SC_R1_WIDE_NPTS
-#define SC_R1_WIDE_NPTS 5  // NPTS from which the kernel is built for 2 CTAs/SM (255 registers, no spills) instead of 3 (168)
+#define SC_R1_WIDE_NPTS 5  // NPTS from which the kernel is built for 2 CTAs/SM (255 registers, no spills)
 #endif
 constexpr uint32_t R1_SLOTS = 4;
 constexpr uint32_t R1_THREADS = 128;
@@ -27,6 +27,9 @@ __global__ void __launch_bounds__(R1_THREADS, (NPTS >= SC_R1_WIDE_NPTS ? 2 : 3))
     __shared__ __align__(8) uint64_t s_full[R1_SLOTS], s_empty[R1_SLOTS];
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // (Measured: parking the accumulators in tensor memory — tcgen05.ld/st around every lazy multiply-accumulate — brings the
+    // kernel to 128 registers and 4 CTAs/SM, bit-exact, but NOT faster: 1.135 ms against 1.11 ms at nv = 24.  The kernel is
+    // bound by the instruction rate of the multiply pipe, not by latency)
     fr::WideAcc accw[NPTS];
 #pragma unroll
     for (int t = 0; t < NPTS; t++) fr::wide_zero(accw[t]);
