@@ -178,6 +178,16 @@ SC_API int sc_gkr_prove(sc_blake2b512_rng *rng, uint32_t dim, uint64_t nnz, cons
                  const uint64_t *f2, const uint64_t *f3, const uint64_t *g, int device, uint64_t *phase1_out,
                  uint64_t *phase2_out, uint64_t *u_out, uint64_t *v_out);
 
+/* n_layers independent GKRRoundSumcheck::prove calls of one dim in ONE call (the layers of a GKR circuit
+ * whose inputs are already known, or a batch of circuits): every array argument holds one pointer (rngs: one state) per layer,
+ * with the meaning it has in sc_gkr_prove.  The uploads of the layers overlap with the initialisers of the previous ones, and
+ * every sumcheck round is issued for all layers before the first result is collected, so the per-round latency is shared by
+ * the batch.  Each layer's outputs are bit-identical to a separate sc_gkr_prove call with the same rng state. */
+SC_API int sc_gkr_prove_batch(uint32_t n_layers, sc_blake2b512_rng *rngs, uint32_t dim, const uint64_t *nnz,
+                              const uint64_t *const *f1_idx, const uint64_t *const *f1_val, const uint64_t *const *f2,
+                              const uint64_t *const *f3, const uint64_t *const *g, int device, uint64_t *const *phase1_out,
+                              uint64_t *const *phase2_out, uint64_t *const *u_out, uint64_t *const *v_out);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Verifier-side counterparts (what the reference's tests call right after proving). */
 /* ListOfProductsOfPolynomials::evaluate (src/ml_sumcheck/data_structures.rs:99-109): the polynomial at `point`

@@ -486,3 +486,28 @@ class GKRRoundSumcheck:
                                        _p64(f2), _p64(f3), _p64(g), device, _p64(m1), _p64(m2), _p64(u), _p64(v)))
         proof = GKRProof([ProverMsg(m1[i]) for i in range(dim)], [ProverMsg(m2[i]) for i in range(dim)])
         return (proof, u, v) if return_challenges else proof
+
+
+    @staticmethod
+    def prove_batch(rngs, f1s, f2s, f3s, gs, device=0):
+        """L independent GKRRoundSumcheck::prove calls of one dim in one library call (sc_gkr_prove_batch): the uploads overlap
+        with the initialisers and every sumcheck round is issued for all layers before the first result is collected.  Each
+        returned GKRProof is bit-identical to a separate prove() with the same rng state."""
+        L = len(f1s)
+        assert L >= 1 and len(rngs) == len(f2s) == len(f3s) == len(gs) == L
+        f2s, f3s, gs = [_elems(x) for x in f2s], [_elems(x) for x in f3s], [_elems(x) for x in gs]
+        dim = _dim_of(f2s[0])
+        for f1, f2, f3, g in zip(f1s, f2s, f3s, gs):
+            assert _dim_of(f2) == dim and _dim_of(f3) == dim and f1.num_vars == 3 * dim and g.shape[0] == dim
+            if not isinstance(rngs[0], Blake2b512Rng):
+                raise SumcheckError(-5, "the batched device path binds the concrete Blake2b512Rng")
+        states = (RngState * L)(*[r.state for r in rngs])
+        nnz = np.array([f1.indices.shape[0] for f1 in f1s], dtype=np.uint64)
+        m1 = [np.zeros((dim, 3, 4), dtype=np.uint64) for _ in range(L)]
+        m2 = [np.zeros((dim, 3, 4), dtype=np.uint64) for _ in range(L)]
+        vp = lambda arrs: (C.c_void_p * L)(*[a.ctypes.data for a in arrs])
+        _check(capi.lib().sc_gkr_prove_batch(L, states, dim, _p64(nnz), vp([f.indices for f in f1s]), vp([f.values for f in f1s]), vp(f2s),
+                                             vp(f3s), vp(gs), device, vp(m1), vp(m2), None, None))
+        for r, st in zip(rngs, states):  # the transcripts advanced inside the call
+            C.memmove(C.byref(r.state), C.byref(st), C.sizeof(RngState))
+        return [GKRProof([ProverMsg(a[i]) for i in range(dim)], [ProverMsg(b[i]) for i in range(dim)]) for a, b in zip(m1, m2)]

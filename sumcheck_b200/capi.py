@@ -68,6 +68,9 @@ SIGNATURES = {
     "sc_gkr_start_phase2_sumcheck": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, U64P, U64P, U64P, C.c_int]),
     "sc_gkr_prove": (C.c_int, [C.POINTER(RngState), C.c_uint32, C.c_uint64, U64P, U64P, U64P, U64P, U64P, C.c_int, U64P, U64P,
                                U64P, U64P]),
+    "sc_gkr_prove_batch": (C.c_int, [C.c_uint32, C.POINTER(RngState), C.c_uint32, U64P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
 }
 
 

@@ -124,7 +124,7 @@ constexpr size_t RES_BCAST_BYTES = 64 * 8 + 64;
 constexpr unsigned long long RES_MAX_PAIRS_DEFAULT = 1ull << 16;
 constexpr uint32_t EAGER_CHUNKS = 8;
 constexpr uint32_t EAGER_SLOT_WORDS = sck::MAX_NPTS * 8 + 8;  // raw sums, then the flag word
-constexpr size_t CACHE_MAX_ENTRIES = 8;
+constexpr size_t CACHE_MAX_ENTRIES = 96;  // a 16-layer GKR batch holds 16 instance slabs, 32 prover slabs, 32 pinned blocks and 32 streams at once
 // Largest block the cache keeps and the most it holds per device.  The nv = 24 one-shot proof (MLSumcheck::prove: create +
 // prove + destroy) allocates a 1.5 GiB and a 1.1 GiB slab: with the first-round limit of 256 MiB both went through
 // cudaMalloc/cudaFree on every call.  180 GB of HBM make 8 GiB of parked slabs cheap;
@@ -280,6 +280,7 @@ struct sc_prover {
     sc_prover* wait_on = nullptr;  // whose mapped result block the round just issued will signal (this or sub)
     uint32_t switch_round = 0;     // first global round run replicated
     bool switched = false;         // ... and this proof has gathered the tables for it
+    bool collect_pending = false;  // prove_round_issue launched a round whose message prove_round_collect has yet to fetch
     bool host_done = false;        // the round just run left its message in h_evals / h_canon (host-side exchange)
     uint32_t** d_peer_tabs = nullptr;  // [3][n_ranks][T] every rank's table pointers in each buffer, as seen from this device
     std::vector<void*> ipc_opened;     // peer slabs mapped through CUDA IPC (multi-process)
@@ -300,13 +301,15 @@ struct sc_prover {
     // Resident rounds (resident_kernel.cuh): set by run_rounds for the proof in flight
     uint32_t res_first = 0;            // first (1-based) round served by the resident kernel; 0 = none
     bool res_running = false;          // the kernel is on the GPU, waiting for fold constants
+    int res_share = 1;                 // independent provers whose resident kernels are on this device at the same time (batches)
     uint32_t res_seq0 = 0, res_last_seq = 0;  // sequence numbers of its first and last round
     unsigned long long res_max_pairs = 0;
     uint32_t *h_res = nullptr, *d_res = nullptr;  // mapped block: [64 x {limb,seq}] constants | [40 x {limb,seq}] sums | error | abort
     uint32_t* d_res_bcast = nullptr;   // device: [64 x {limb,seq}] + abort word
     unsigned int* d_res_counters = nullptr;
     long long* d_res_prof = nullptr;   // SC_RES_PROF=1: per-round cycle counts of CTA 0
-    double res_host_us[64][3] = {};    // ... and host-side microseconds per resident round: constants out, wait, finish
+    double res_host_us[64][3] = {};
+    double res_t0 = 0, res_t1 = 0;     // (profiling) time stamps between resident_post and resident_collect    // ... and host-side microseconds per resident round: constants out, wait, finish
     void* adopted = nullptr;           // a device block whose ownership was handed to this handle (freed on destroy)
     size_t adopted_bytes = 0;
 };
@@ -766,11 +769,15 @@ struct BounceLease {
         B = nullptr;
     }
     cudaError_t acquire(const sc_prover* p, const uint64_t* const* tables) {
-        if (p->N * 32 < ((size_t)4 << 20) || getenv("SC_NO_BOUNCE")) return cudaSuccess;
+        if (p->N * 32 < ((size_t)4 << 20)) return cudaSuccess;
+        return acquire_raw(p->device, (const void* const*)tables, p->T);
+    }
+    cudaError_t acquire_raw(int device, const void* const* ptrs, uint32_t n) {
+        if (getenv("SC_NO_BOUNCE")) return cudaSuccess;
         bool pageable = false;
-        for (uint32_t j = 0; j < p->T && !pageable; j++) pageable = host_pointer_is_pageable(tables[j]);
+        for (uint32_t j = 0; j < n && !pageable; j++) pageable = host_pointer_is_pageable(ptrs[j]);
         if (!pageable) return cudaSuccess;
-        Bounce& b = g_bounce[p->device & 63];
+        Bounce& b = g_bounce[device & 63];
         b.mu.lock();
         B = &b;
         for (int k = 0; k < BOUNCE_SLOTS; k++) {
@@ -950,10 +957,12 @@ int resident_launch(sc_prover* p) {
     // ranks sharing a device (sc_prover_create_multi with a repeated device id): their resident kernels wait for each other's
     // partial sums, so ALL of them must fit on the device at once — next to the launch-per-round kernels of a rank that is
     // still a round behind (half of the device is left to those)
+    const int share = comm_device_share(p) > p->res_share ? comm_device_share(p) : p->res_share;
     if (comm_device_share(p) > 1) cap /= 2ull * (unsigned long long)comm_device_share(p);
+    else if (share > 1) cap = cap / (unsigned long long)share;  // a batch: the kernels do not depend on each other, they only share the SMs
     if (cap < 1) cap = 1;
     const int grid = (int)(need < cap ? (need ? need : 1) : cap);
-    cudaError_t e = sck::launch_resident(d, grid, q, p->stream, comm_device_share(p) == 1);
+    cudaError_t e = sck::launch_resident(d, grid, q, p->stream, share == 1);
     if (e != cudaSuccess) return fail(SC_ERR_CUDA, "resident kernel launch: %s", cudaGetErrorString(e));
     p->launches++;
     p->res_running = true;
@@ -973,7 +982,9 @@ void resident_abort(sc_prover* p) {
 
 // One round served by the resident kernel: prove_round's state machine, then fold constants out / raw sums in.
 // `w` is the handle whose kernel is on the GPU: p itself, or the replicated sub-prover of a sharded p.
-int resident_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
+int resident_collect(sc_prover* p, sc_prover* w, const uint64_t* r);
+
+int resident_post(sc_prover* p, sc_prover* w, const uint64_t* r) {
     p->randomness.insert(p->randomness.end(), r, r + 4);  // prover.rs:82
     p->round += 1;
     if (p->round > p->nv) return fail(SC_ERR_PANIC_NOT_ACTIVE, "Prover is not active");
@@ -998,7 +1009,16 @@ int resident_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
             __atomic_store_n(hc + k * 8 + 2 * i + 1, (uint64_t)(c.l[i] >> 32) | ((uint64_t)seq << 32), __ATOMIC_RELAXED);
         }
     }
-    const double h1 = prof ? now_us() : 0;
+    w->res_t0 = h0;
+    w->res_t1 = prof ? now_us() : 0;
+    return SC_OK;
+}
+
+int resident_collect(sc_prover* p, sc_prover* w, const uint64_t* r) {
+    const uint32_t seq = w->seq, d = p->d;
+    const bool prof = w->d_res_prof != nullptr;
+    auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    const double h0 = w->res_t0, h1 = w->res_t1;
     // wait for the d sums: unreduced 17-limb integers, every limb one {limb, seq} word
     const uint64_t* hs = (const uint64_t*)((uint8_t*)w->h_res + RES_OFF_SUMS);
     const uint32_t n_words = d * 17;
@@ -1054,8 +1074,17 @@ int resident_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
     return SC_OK;
 }
 
+int resident_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
+    int rc = resident_post(p, w, r);
+    if (rc) return rc;
+    return resident_collect(p, w, r);
+}
+
 // prove_round state machine (prover.rs:78-98) + device round + D2H of the d+1 results into the pinned buffers.
-int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
+// Split in two so that a batch driver (capi_gkr.inc sc_gkr_prove_batch) can issue the round of many independent provers before
+// it collects the first result: prove_round_issue launches, prove_round_collect waits for the message and finishes it.
+int prove_round_issue(sc_prover* p, const uint64_t* r_or_null) {
+    p->collect_pending = false;
     if (r_or_null) {
         if (p->round == 0) return fail(SC_ERR_PANIC_FIRST_ROUND_MSG, "first round should be prover first.");
         p->randomness.insert(p->randomness.end(), r_or_null, r_or_null + 4);
@@ -1102,7 +1131,7 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
         p->direct_active = true;
         if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));  // the round's work ran during the upload
         if (p->res_first && p->round + 1 == p->res_first) return resident_launch(p);
-        return SC_OK;
+        return SC_OK;  // nothing left to collect
     }
     if (p->comm) {
         rc = sharded_round(p, r_or_null);
@@ -1117,6 +1146,7 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
         p->host_done = false;
         return SC_OK;
     }
+    p->collect_pending = true;
     if (p->res_first && p->round + 1 == p->res_first) {
         // the next round is the first resident one: queue the kernel now, so that it is already polling when this
         // round's challenge has been drawn
@@ -1131,6 +1161,12 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
             }
         }
     }
+    return SC_OK;
+}
+
+int prove_round_collect(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
+    if (!p->collect_pending) return SC_OK;
+    p->collect_pending = false;
     if (p->direct_active) {
         // the last block wrote the message into mapped pinned memory and then the flag: spin instead of copy + sync
         sc_prover* w = (p->comm && p->wait_on) ? p->wait_on : p;
@@ -1163,6 +1199,12 @@ int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
         memcpy(p->h_prev.data(), p->h_evals, (size_t)(p->d + 1) * 32);
     }
     return SC_OK;
+}
+
+int prove_round_impl(sc_prover* p, const uint64_t* r_or_null, bool sync_out) {
+    int rc = prove_round_issue(p, r_or_null);
+    if (rc) return rc;
+    return prove_round_collect(p, r_or_null, sync_out);
 }
 
 // First round (1-based) handled by the fused tail kernel, or nv+1 when the tail is not used.
@@ -1300,6 +1342,48 @@ int run_rounds(sc_prover* p, b2::State* st, uint64_t* evals_out, uint64_t* chall
         cudaStreamSynchronize(p->stream);
         for (uint32_t i = 0; i < nv; i++) cudaEventElapsedTime(&p->round_ms[i], p->ev[2 * i], p->ev[2 * i + 1]);
     }
+    return SC_OK;
+}
+
+// The same loop for SEVERAL independent provers of one shape (the layers of sc_gkr_prove_batch), each with its own transcript:
+// every round is issued for all provers before the first result is collected, so the ~8 us a latency-bound round costs is
+// shared by the whole batch instead of paid once per prover.
+int run_rounds_batch(std::vector<sc_prover*>& ps, std::vector<b2::State*>& sts, std::vector<uint64_t*>& evals_out,
+                     std::vector<uint64_t*>& challenges_out) {
+    const size_t L = ps.size();
+    if (L == 1) return run_rounds(ps[0], sts[0], evals_out[0], challenges_out[0]);
+    const uint32_t nv = ps[0]->nv, d = ps[0]->d;
+    std::vector<uint8_t> msg(8 + 32 * (size_t)(d + 1));
+    b2::put_u64(msg.data(), d + 1);
+    std::vector<uint64_t> r(L * 4, 0);
+    for (sc_prover* p : ps) p->res_first = resident_first_round(p);
+    auto bail = [&](int rc) {
+        for (sc_prover* p : ps) {
+            resident_abort(p);
+            p->res_first = 0;
+        }
+        return rc;
+    };
+    for (uint32_t i = 0; i < nv; i++) {
+        for (size_t l = 0; l < L; l++) {
+            sc_prover* p = ps[l];
+            const uint64_t* rl = i ? &r[l * 4] : nullptr;
+            int rc = (p->res_first && i + 1 >= p->res_first) ? resident_post(p, p, rl) : prove_round_issue(p, rl);
+            if (rc) return bail(rc);
+        }
+        for (size_t l = 0; l < L; l++) {
+            sc_prover* p = ps[l];
+            const uint64_t* rl = i ? &r[l * 4] : nullptr;
+            int rc = (p->res_first && i + 1 >= p->res_first) ? resident_collect(p, p, rl) : prove_round_collect(p, rl, true);
+            if (rc) return bail(rc);
+            memcpy(evals_out[l] + (size_t)i * (d + 1) * 4, p->h_evals, (size_t)(d + 1) * 32);
+            memcpy(msg.data() + 8, p->h_canon, (size_t)(d + 1) * 32);
+            b2::update(sts[l], msg.data(), msg.size());
+            b2::sample_fr(sts[l], &r[l * 4]);
+            memcpy(challenges_out[l] + (size_t)i * 4, &r[l * 4], 32);
+        }
+    }
+    for (sc_prover* p : ps) p->res_first = 0;
     return SC_OK;
 }
 

@@ -547,3 +547,29 @@ def test_gkr_config5_dim18(orc):
     assert np.array_equal(np.stack([m.evaluations for m in proof.phase2_sumcheck_msgs]), m2)
     vu, vv, exp = orc.gkr_verify(orc.Rng(), dim, m1, m2, proof.extract_sum())
     assert orc.gkr_verify_subclaim(dim, f1s.indices, f1s.values, f2, f3, g, vu, vv, exp)
+
+
+@pytest.mark.parametrize("dim,L", [(4, 3), (9, 5), (13, 4)])
+def test_gkr_batch_matches_separate_proofs(orc, dim, L):
+    """sc_gkr_prove_batch: L layers in one call (rounds of all layers issued before the first is collected) == L separate
+    oracle proofs, bit for bit, including the transcripts afterwards; different sparsities per layer."""
+    rnd = random.Random(1234 + dim)
+    f1s, f2s, f3s, gs, want = [], [], [], [], []
+    for l in range(L):
+        f1, f2, f3, g = random_gkr(500 + 10 * dim + l, dim, nnz=rnd.choice([1, 1 << (dim - 1), 1 << dim]))
+        idx, val, f2a, f3a, ga = gkr_arrays(f1, f2, f3, g)
+        f1s.append(sc.SparseMultilinearExtension(3 * dim, idx, val)); f2s.append(f2a); f3s.append(f3a); gs.append(ga)
+        org = orc.Rng()
+        org.feed_bytes(bytes([l]))
+        m1, m2, _, _ = orc.gkr_prove(org, dim, idx, val, f2a, f3a, ga)
+        want.append((m1, m2, org.next_u64()))
+    rngs = []
+    for l in range(L):
+        r = sc.Blake2b512Rng.setup()
+        r.feed(bytes([l]))
+        rngs.append(r)
+    proofs = sc.GKRRoundSumcheck.prove_batch(rngs, f1s, f2s, f3s, gs)
+    for l in range(L):
+        assert np.array_equal(np.stack([m.evaluations for m in proofs[l].phase1_sumcheck_msgs]), want[l][0]), f"layer {l} phase 1"
+        assert np.array_equal(np.stack([m.evaluations for m in proofs[l].phase2_sumcheck_msgs]), want[l][1]), f"layer {l} phase 2"
+        assert rngs[l].next_u64() == want[l][2]
