@@ -480,8 +480,32 @@ class GKRRoundSumcheck:
         u = np.zeros((dim, 4), dtype=np.uint64)
         v = np.zeros((dim, 4), dtype=np.uint64)
         if not isinstance(rng, Blake2b512Rng):
-            raise SumcheckError(-5, "the device path binds the concrete Blake2b512Rng; drive the phases via "
-                                    "initialize_phase_*/start_phase*_sumcheck + prove_round for other FeedableRNGs")
+            # generic R: FeedableRNG (mod.rs:93): the reference's own loop, every step on the device — the four phase
+            # helpers, prove_round per round, f2.evaluate(u); the transcript stays with the caller's rng object
+            h_g, f1_g = initialize_phase_one(f1, f3, g, device)                     # mod.rs:106
+            ps = start_phase1_sumcheck(h_g, f2, device)                            # mod.rs:107
+            vm, msgs1, u_l = None, [], []
+            for _ in range(dim):                                                    # mod.rs:111-119
+                pm = IPForMLSumcheck.prove_round(ps, vm)
+                rng.feed(pm.serialize_uncompressed())
+                msgs1.append(pm)
+                vm = IPForMLSumcheck.sample_round(rng)
+                u_l.append(vm.randomness)
+            u = np.stack(u_l)
+            f1_gu = initialize_phase_two(f1_g, u, device)                           # mod.rs:121
+            f2_poly = ListOfProductsOfPolynomials.new(dim)
+            f2_poly.add_product([f2], FR_ONE)
+            f2_u = f2_poly.evaluate(u, device)                                      # f2.evaluate(&u), mod.rs:122
+            ps = start_phase2_sumcheck(f1_gu, f3, f2_u, device)
+            vm, msgs2, v_l = None, [], []
+            for _ in range(dim):                                                    # mod.rs:126-133
+                pm = IPForMLSumcheck.prove_round(ps, vm)
+                rng.feed(pm.serialize_uncompressed())
+                msgs2.append(pm)
+                vm = IPForMLSumcheck.sample_round(rng)
+                v_l.append(vm.randomness)
+            proof = GKRProof(msgs1, msgs2)
+            return (proof, u, np.stack(v_l)) if return_challenges else proof
         _check(capi.lib().sc_gkr_prove(C.byref(rng.state), dim, f1.indices.shape[0], _p64(f1.indices), _p64(f1.values),
                                        _p64(f2), _p64(f3), _p64(g), device, _p64(m1), _p64(m2), _p64(u), _p64(v)))
         proof = GKRProof([ProverMsg(m1[i]) for i in range(dim)], [ProverMsg(m2[i]) for i in range(dim)])

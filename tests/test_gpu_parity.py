@@ -573,3 +573,19 @@ def test_gkr_batch_matches_separate_proofs(orc, dim, L):
         assert np.array_equal(np.stack([m.evaluations for m in proofs[l].phase1_sumcheck_msgs]), want[l][0]), f"layer {l} phase 1"
         assert np.array_equal(np.stack([m.evaluations for m in proofs[l].phase2_sumcheck_msgs]), want[l][1]), f"layer {l} phase 2"
         assert rngs[l].next_u64() == want[l][2]
+
+
+def test_gkr_generic_feedable_rng(orc):
+    """GKRRoundSumcheck::prove<R: FeedableRNG> with an rng the library cannot see into (gkr mod.rs:93): the reference's loop
+    runs on the host side of the mirror, every step (phase initialisers, prove_round, f2.evaluate(u)) on the device."""
+    class Wrapped:  # same stream as Blake2b512Rng, but opaque to the library
+        def __init__(self): self.inner = sc.Blake2b512Rng.setup(); self.state = self.inner.state
+        def feed(self, b): self.inner.feed(b)
+    for dim, nnz in [(3, 5), (7, 1 << 7)]:
+        f1, f2, f3, g = random_gkr(900 + dim, dim, nnz=nnz)
+        idx, val, f2a, f3a, ga = gkr_arrays(f1, f2, f3, g)
+        proof, u, v = sc.GKRRoundSumcheck.prove(Wrapped(), sc.SparseMultilinearExtension(3 * dim, idx, val), f2a, f3a, ga, return_challenges=True)
+        m1, m2, ou, ov = orc.gkr_prove(orc.Rng(), dim, idx, val, f2a, f3a, ga)
+        assert np.array_equal(np.stack([m.evaluations for m in proof.phase1_sumcheck_msgs]), m1)
+        assert np.array_equal(np.stack([m.evaluations for m in proof.phase2_sumcheck_msgs]), m2)
+        assert np.array_equal(u, ou) and np.array_equal(v, ov)
