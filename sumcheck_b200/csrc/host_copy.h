@@ -1,9 +1,8 @@
 // Host side of the upload of caller tables that live in PAGEABLE memory (a Rust Vec<F>): prover_init's deep copy
 // (prover.rs:55-59) becomes pageable -> pinned bounce slot -> HBM.  cudaMemcpyAsync from pageable memory runs at 11 GB/s on
 // the B200 box (one driver thread staging through its own bounce buffer); the PCIe 5 x16 link carries 55 GB/s.  Measured
-// there (tools/microbench/hostprobe.cu, 16 vCPUs): 12 threads filling pinned slots with non-temporal stores reach 65 GB/s
-// alone and 47 GB/s while the DMA engine reads the previous slot (host DRAM bandwidth is shared by the copy's reads, its
-// writes and the DMA's reads; plain memcpy pays a read-for-ownership of the destination on top: 37 GB/s).
+// there (tools/microbench/hostprobe.cu, 16 vCPUs): 12 threads filling pinned slots reach 65 GB/s alone and 47 GB/s while the
+// DMA engine reads the previous slot (host DRAM bandwidth is shared by the copy's reads, its writes and the DMA's reads).
 // This is a memcpy, not a CPU path of the protocol: no field arithmetic happens here.
 #pragma once
 #include <atomic>
@@ -39,9 +38,17 @@ inline bool have_avx2() {
 }
 #endif
 
+// Cached stores by default; SC_COPY_NT=1 selects the streaming stores.  Measured end to end on the B200 box (one-shot nv = 24
+// proof from pageable tables, tools/e2e_sweep.sh): 8 threads + cached stores 33.2 ms, 12 threads + streaming stores 35.3 ms,
+// PCIe alone 29.1 ms — the DMA engine can take freshly written lines from the last-level cache instead of DRAM.
+inline bool use_nt() {
+    static const bool v = getenv("SC_COPY_NT") && atoi(getenv("SC_COPY_NT")) != 0;
+    return v;
+}
+
 inline void copy_piece(uint8_t* dst, const uint8_t* src, size_t n) {
 #if defined(__x86_64__)
-    if (have_avx2() && ((uintptr_t)dst & 31) == 0) {
+    if (use_nt() && have_avx2() && ((uintptr_t)dst & 31) == 0) {
         const size_t body = n & ~(size_t)127;
         copy_nt_avx2(dst, src, body);
         if (n > body) memcpy(dst + body, src + body, n - body);
@@ -62,8 +69,9 @@ public:
 
     // dst[0..n) = src[0..n), split into pieces taken by the workers and the calling thread; returns when all are done
     void copy(uint8_t* dst, const uint8_t* src, size_t n) {
-        const size_t piece = (size_t)1 << 20;
-        if (workers_.empty() || n <= 2 * piece) {
+        size_t piece = (size_t)1 << 20;
+        if (n < piece * (workers_.size() + 1)) piece = ((n / (workers_.size() + 1)) + 4095) & ~(size_t)4095;  // small slots: one piece per thread
+        if (workers_.empty() || n <= (size_t)256 << 10) {
             copy_piece(dst, src, n);
             return;
         }
@@ -94,7 +102,7 @@ public:
 private:
     Pool() {
         unsigned hw = std::thread::hardware_concurrency();
-        int want = hw >= 16 ? 12 : (hw > 2 ? (int)(hw * 3 / 4) : 1);
+        int want = hw >= 4 ? (int)(hw / 2) : 1;  // half of the cores: more threads only add DRAM contention (tools/e2e_sweep.sh)
         if (const char* e = getenv("SC_COPY_THREADS")) want = atoi(e);
         if (want < 1) want = 1;
         if (want > 64) want = 64;

@@ -722,13 +722,32 @@ int prescale_tables(sc_prover* p) {
 
 // ---- table upload --------------------------------------------------------------------------------------------------
 // Pinned bounce slots for pageable sources (host_copy.h), shared by all handles of a device; an upload holds the mutex.
-constexpr size_t BOUNCE_SLOT_BYTES = (size_t)16 << 20;
-constexpr int BOUNCE_SLOTS = 4;
+constexpr int BOUNCE_MAX_SLOTS = 16;
+size_t bounce_slot_bytes() {
+    static const size_t v = [] {
+        const char* e = getenv("SC_BOUNCE_SLOT_KB");
+        size_t kb = e ? strtoull(e, nullptr, 10) : 16384;
+        if (kb < 64) kb = 64;
+        if (kb > (1u << 20)) kb = 1u << 20;
+        return kb << 10;
+    }();
+    return v;
+}
+int bounce_slots() {
+    static const int v = [] {
+        const char* e = getenv("SC_BOUNCE_SLOTS");
+        int n = e ? atoi(e) : 4;
+        return n < 2 ? 2 : (n > BOUNCE_MAX_SLOTS ? BOUNCE_MAX_SLOTS : n);
+    }();
+    return v;
+}
+#define BOUNCE_SLOT_BYTES bounce_slot_bytes()
+#define BOUNCE_SLOTS bounce_slots()
 struct Bounce {
     std::mutex mu;
-    uint8_t* slot[BOUNCE_SLOTS] = {};
-    cudaEvent_t ev[BOUNCE_SLOTS] = {};
-    bool busy[BOUNCE_SLOTS] = {};
+    uint8_t* slot[BOUNCE_MAX_SLOTS] = {};
+    cudaEvent_t ev[BOUNCE_MAX_SLOTS] = {};
+    bool busy[BOUNCE_MAX_SLOTS] = {};
     size_t k = 0;
 };
 Bounce g_bounce[64];
