@@ -38,11 +38,12 @@ inline bool have_avx2() {
 }
 #endif
 
-// Cached stores by default; SC_COPY_NT=1 selects the streaming stores.  Measured end to end on the B200 box (one-shot nv = 24
-// proof from pageable tables, tools/e2e_sweep.sh): 8 threads + cached stores 33.2 ms, 12 threads + streaming stores 35.3 ms,
-// PCIe alone 29.1 ms — the DMA engine can take freshly written lines from the last-level cache instead of DRAM.
+// Streaming stores by default; SC_COPY_NT=0 selects cached stores.  Measured end to end on the B200 box (one-shot nv = 24 proof
+// from pageable tables, tools/e2e_sweep.sh; PCIe alone 29.1 ms): 12 threads + streaming stores 34.8-35.3 ms in every run; 8
+// threads + cached stores 33.2 ms in one process and 64 ms in another (the DMA engine sometimes takes the fresh lines from the
+// last-level cache and sometimes fights the copy for them) — the stable setting is the default.
 inline bool use_nt() {
-    static const bool v = getenv("SC_COPY_NT") && atoi(getenv("SC_COPY_NT")) != 0;
+    static const bool v = !(getenv("SC_COPY_NT") && atoi(getenv("SC_COPY_NT")) == 0);
     return v;
 }
 
@@ -102,7 +103,7 @@ public:
 private:
     Pool() {
         unsigned hw = std::thread::hardware_concurrency();
-        int want = hw >= 4 ? (int)(hw / 2) : 1;  // half of the cores: more threads only add DRAM contention (tools/e2e_sweep.sh)
+        int want = hw >= 16 ? 12 : (hw > 2 ? (int)(hw * 3 / 4) : 1);
         if (const char* e = getenv("SC_COPY_THREADS")) want = atoi(e);
         if (want < 1) want = 1;
         if (want > 64) want = 64;
