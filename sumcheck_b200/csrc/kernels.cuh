@@ -181,23 +181,30 @@ struct RegAccs {
 };
 // ... or parked in tensor memory (tma_round1.cuh TmemAccs): same interface.
 
-template <int NPTS, bool ILP = false, class ACCS>
+// SKIP: -1 = p.skip1 decides at run time, 0 / 1 = known when the kernel is built (round 1 never skips P(1), the tensor-core fold
+// rounds always do).  SIMPLE: ONE product whose coefficient is deferred to the end of the round and a single launch per round
+// (t0 == 0) — then nothing about the coefficient or the first evaluation point is left to decide per pair.  With compile-time
+// first / last / kdeg (callers that unroll over the multiplicands of a single product) the whole body is branch-free.
+template <int NPTS, bool ILP = false, int SKIP = -1, bool SIMPLE = false, class ACCS>
 __device__ __forceinline__ void consume_pair_acc(const RoundParams& p, uint32_t k, bool first, bool last, uint32_t kdeg, const Fr& v0,
                                                  const Fr& v1, Fr (&prod)[NPTS], ACCS& accs) {
+    const bool skip1 = SKIP < 0 ? (p.skip1 != 0) : (SKIP != 0);
     // prover.rs:119-124: start = table[2b], step = table[2b+1] - start; product[t] *= start; start += step
     Fr step = fr::sub(v1, v0);
     Fr cur = v0;
-    for (uint32_t s = 0; s < p.t0; s++) cur = fr::add(cur, step);  // only for d+1 > MAX_NPTS
-    if (first && !p.defer_coeff && !(p.prod_scaled && p.prod_scaled[k])) {  // c_k * prod_j(...): scale the first multiplicand's line once
-        Fr c = fr::load(p.coeffs + 8 * k);
-        cur = fr::mul(cur, c);
-        step = fr::mul(step, c);
+    if (!SIMPLE) {
+        for (uint32_t s = 0; s < p.t0; s++) cur = fr::add(cur, step);  // only for d+1 > MAX_NPTS
+        if (first && !p.defer_coeff && !(p.prod_scaled && p.prod_scaled[k])) {  // c_k * prod_j(...): scale the first multiplicand's line once
+            Fr c = fr::load(p.coeffs + 8 * k);
+            cur = fr::mul(cur, c);
+            step = fr::mul(step, c);
+        }
     }
     // slot s holds evaluation point t0+s, or with skip1 the points 0, 2, 3, ..: one extra step after slot 0
 #define SC_NEXT_POINT(t)                                        \
     if ((t) + 1 < NPTS) {                                       \
         cur = fr::add(cur, step);                               \
-        if ((t) == 0 && p.skip1) cur = fr::add(cur, step);      \
+        if ((t) == 0 && skip1) cur = fr::add(cur, step);        \
     }
     if (first && last) {  // single multiplicand: contributes its value itself
         accs.begin();
@@ -219,7 +226,7 @@ __device__ __forceinline__ void consume_pair_acc(const RoundParams& p, uint32_t 
             accs.mac(t, prod[t], cur);
             SC_NEXT_POINT(t)
         }
-    } else if (ILP && p.skip1) {
+    } else if (ILP && skip1) {
         // latency-bound callers: the NPTS points of this multiplicand in ONE out-of-line call (interleaved carry chains)
         fr::FrN<NPTS> a, b;
 #pragma unroll
@@ -236,7 +243,7 @@ __device__ __forceinline__ void consume_pair_acc(const RoundParams& p, uint32_t 
         // points only k+1 values need a multiply; the others follow by finite differences (integer
         // combinations, exact): k = 2: q(t) = 3(q(t-1) - q(t-2)) + q(t-3);  k = 3: q(t) = 4(q(t-1) + q(t-3)) -
         // 6 q(t-2) - q(t-4).  Saves one of the four multiplies of round 1 at degree 3.
-        const bool consecutive = !p.skip1;
+        const bool consecutive = !skip1;
 #pragma unroll
         for (int t = 0; t < NPTS; t++) {
             if (t >= 3 && consecutive && kdeg == 2) {

@@ -353,18 +353,18 @@ cudaError_t launch_round(sc_prover* p, bool fold, const sck::RoundParams& rp) {
 
 // Round 1 on the TMA-staged kernel (tma_round1.cuh).  Resident CTAs per SM from the function attributes (registers,
 // shared memory): see tail.cu tc_prepare for why the occupancy API is not used.
-template <int NPTS>
-cudaError_t launch_round1_tma(sc_prover* p, const sck::RoundParams& rp) {
+template <int NPTS, int M = 0>
+cudaError_t launch_round1_tma_m(sc_prover* p, const sck::RoundParams& rp) {
     static bool ready_dev[64] = {};
     static int blocks_dev[64] = {};
     const int dev = p->device & 63;
     if (!ready_dev[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(sck::round1_tma_kernel<NPTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sck::R1_DYN_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(sck::round1_tma_kernel<NPTS, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sck::R1_DYN_SMEM);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(sck::round1_tma_kernel<NPTS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(sck::round1_tma_kernel<NPTS, M>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         cudaFuncAttributes fa;
-        e = cudaFuncGetAttributes(&fa, sck::round1_tma_kernel<NPTS>);
+        e = cudaFuncGetAttributes(&fa, sck::round1_tma_kernel<NPTS, M>);
         if (e != cudaSuccess) return e;
         int regs_sm = 0, smem_sm = 0;
         cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, p->device);
@@ -374,7 +374,7 @@ cudaError_t launch_round1_tma(sc_prover* p, const sck::RoundParams& rp) {
         int blocks = regs_sm / regs_cta;
         if (smem_sm / smem_cta < blocks) blocks = smem_sm / smem_cta;
         if (blocks < 1) blocks = 1;
-        if (getenv("SC_DEBUG")) fprintf(stderr, "round1_tma_kernel<%d>: %d CTAs/SM (regs %d)\n", NPTS, blocks, fa.numRegs);
+        if (getenv("SC_DEBUG")) fprintf(stderr, "round1_tma_kernel<%d,%d>: %d CTAs/SM (regs %d)\n", NPTS, M, blocks, fa.numRegs);
         blocks_dev[dev] = blocks;
         ready_dev[dev] = true;
     }
@@ -383,8 +383,22 @@ cudaError_t launch_round1_tma(sc_prover* p, const sck::RoundParams& rp) {
     if (cap > (unsigned long long)p->max_grid) cap = p->max_grid;
     const int grid = (int)(n_tiles < cap ? n_tiles : cap);
     p->launches++;
-    sck::round1_tma_kernel<NPTS><<<grid, sck::R1_THREADS, sck::R1_DYN_SMEM, p->stream>>>(rp);
+    sck::round1_tma_kernel<NPTS, M><<<grid, sck::R1_THREADS, sck::R1_DYN_SMEM, p->stream>>>(rp);
     return cudaGetLastError();
+}
+
+// One product of M = NPTS - 1 multiplicands with a deferred coefficient (the shape of BASELINE configs 2, 3 and of both GKR
+// phases): the build with the loops over products and multiplicands unrolled.  Anything else: the CSR-driven kernel.
+bool single_product_shape(const sc_prover* p, const sck::RoundParams& rp, uint32_t m) {
+    static const bool off = getenv("SC_NO_SPECIALISE") != nullptr;
+    return !off && p->n_products == 1 && rp.defer_coeff && !rp.prod_scaled && rp.t0 == 0 && p->h_nnz == m && p->d == m;
+}
+// (Measured at nv = 24, degree 3: the unrolled build helps the tensor-core fold kernel by 1-3 % — round 2 0.697 -> 0.678 ms — but
+// makes round 1 MUCH slower, 1.09 -> 1.68 ms: its fully inlined body, three times as long once unrolled, no longer fits the
+// instruction cache.  Round 1 therefore always runs the CSR-driven build.)
+template <int NPTS>
+cudaError_t launch_round1_tma(sc_prover* p, const sck::RoundParams& rp) {
+    return launch_round1_tma_m<NPTS, 0>(p, rp);
 }
 
 void set_exchange_params(sc_prover* p, sck::RoundParams& rp);  // capi_multi.inc
@@ -460,7 +474,8 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
             rp.tmaps = p->d_maps + (size_t)p->cur * p->T * sizeof(CUtensorMap);
             p->launches++;
             p->tc_rounds++;
-            e = sck::launch_fold_round_tc(p->d, g_dev[p->device].sms, p->max_grid, rp, p->stream);
+            e = sck::launch_fold_round_tc(p->d, (single_product_shape(p, rp, 2) || single_product_shape(p, rp, 3)) ? p->d : 0, g_dev[p->device].sms,
+                                          p->max_grid, rp, p->stream);
         } else
         switch (p->d) {
             case 1: e = launch_round<1>(p, true, rp); break;

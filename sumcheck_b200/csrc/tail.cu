@@ -47,7 +47,7 @@ cudaError_t launch_fold_round(uint32_t npts, int grid, const RoundParams& rp, cu
 // TMA + tensor-core fold rounds (tc_round.cuh): 128 threads, TC_DYN_SMEM bytes of dynamic shared memory
 unsigned long long tc_min_pairs() { return TC_MIN_PAIRS; }
 
-template <int NPTS>
+template <int NPTS, int M = 0>
 static cudaError_t tc_prepare(int* occ) {
     static bool ready_dev[64] = {};
     static int blocks_dev[64] = {};
@@ -57,17 +57,17 @@ static cudaError_t tc_prepare(int* occ) {
     bool& ready = ready_dev[dev];  // function attributes are per device
     int& blocks = blocks_dev[dev];
     if (!ready) {
-        cudaError_t e = cudaFuncSetAttribute(round_tc_kernel<NPTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_DYN_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(round_tc_kernel<NPTS, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_DYN_SMEM);
         if (e != cudaSuccess) return e;
         // three CTAs of ~58 KB each per SM: ask for the largest shared-memory carve-out (the default heuristic sizes it
         // for one CTA and would leave the SM with a single resident block)
-        e = cudaFuncSetAttribute(round_tc_kernel<NPTS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(round_tc_kernel<NPTS, M>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         // Resident CTAs per SM, by hand: cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel on
         // B200 whatever the shared-memory size (measured; three CTAs do co-reside and run 2x faster than one), so the
         // limits are taken from the function and device attributes: registers, shared memory, tensor-memory columns.
         cudaFuncAttributes fa;
-        e = cudaFuncGetAttributes(&fa, round_tc_kernel<NPTS>);
+        e = cudaFuncGetAttributes(&fa, round_tc_kernel<NPTS, M>);
         if (e != cudaSuccess) return e;
         int regs_sm = 0, smem_sm = 0;
         cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
@@ -79,7 +79,7 @@ static cudaError_t tc_prepare(int* occ) {
         if ((int)(512 / TC_TMEM_COLS) < blocks) blocks = 512 / TC_TMEM_COLS;
         if (blocks < 1) blocks = 1;
         if (getenv("SC_DEBUG"))
-            fprintf(stderr, "round_tc_kernel<%d>: %d CTAs/SM (regs %d, static smem %zu, dynamic smem %zu)\n", NPTS, blocks, fa.numRegs,
+            fprintf(stderr, "round_tc_kernel<%d,%d>: %d CTAs/SM (regs %d, static smem %zu, dynamic smem %zu)\n", NPTS, M, blocks, fa.numRegs,
                     fa.sharedSizeBytes, (size_t)TC_DYN_SMEM);
         if (const char* f = getenv("SC_TC_OCC")) blocks = atoi(f);
         ready = true;
@@ -88,13 +88,14 @@ static cudaError_t tc_prepare(int* occ) {
     return cudaSuccess;
 }
 
-cudaError_t launch_fold_round_tc(uint32_t npts, int sms, int max_grid, const RoundParams& rp, cudaStream_t stream) {
+cudaError_t launch_fold_round_tc(uint32_t npts, uint32_t m, int sms, int max_grid, const RoundParams& rp, cudaStream_t stream) {
     int occ = 1;
     cudaError_t e;
+    const bool s2 = m == 2 && npts == 2, s3 = m == 3 && npts == 3;  // the single-product builds
     switch (npts) {
         case 1: e = tc_prepare<1>(&occ); break;
-        case 2: e = tc_prepare<2>(&occ); break;
-        case 3: e = tc_prepare<3>(&occ); break;
+        case 2: e = s2 ? tc_prepare<2, 2>(&occ) : tc_prepare<2>(&occ); break;
+        case 3: e = s3 ? tc_prepare<3, 3>(&occ) : tc_prepare<3>(&occ); break;
         case 4: e = tc_prepare<4>(&occ); break;
         case 5: e = tc_prepare<5>(&occ); break;
         default: return cudaErrorInvalidValue;
@@ -106,8 +107,14 @@ cudaError_t launch_fold_round_tc(uint32_t npts, int sms, int max_grid, const Rou
     const int grid = (int)(n_tiles < cap ? n_tiles : cap);
     switch (npts) {
         case 1: round_tc_kernel<1><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp); break;
-        case 2: round_tc_kernel<2><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp); break;
-        case 3: round_tc_kernel<3><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp); break;
+        case 2:
+            if (s2) round_tc_kernel<2, 2><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp);
+            else round_tc_kernel<2><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp);
+            break;
+        case 3:
+            if (s3) round_tc_kernel<3, 3><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp);
+            else round_tc_kernel<3><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp);
+            break;
         case 4: round_tc_kernel<4><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp); break;
         default: round_tc_kernel<5><<<grid, TC_THREADS, TC_DYN_SMEM, stream>>>(rp); break;
     }

@@ -57,7 +57,8 @@ int fold_round_occupancy(uint32_t npts);
 int fold_round_threads();
 cudaError_t launch_fold_round(uint32_t npts, int grid, const RoundParams& rp, cudaStream_t stream);
 unsigned long long tc_min_pairs();
-cudaError_t launch_fold_round_tc(uint32_t npts, int sms, int max_grid, const RoundParams& rp, cudaStream_t stream);
+// m > 0: the single-product build (one product of m == npts multiplicands, deferred coefficient); 0: the CSR-driven build
+cudaError_t launch_fold_round_tc(uint32_t npts, uint32_t m, int sms, int max_grid, const RoundParams& rp, cudaStream_t stream);
 cudaError_t launch_tail(uint32_t degree, const TailParams& tp, cudaStream_t stream);
 
 }  // namespace sck

@@ -33,7 +33,9 @@ constexpr uint32_t TC_TMEM_COLS = 2 * tcf::ACC_COLS;  // power of two >= 32
 constexpr size_t TC_DYN_SMEM = (size_t)TC_SLOTS * tcf::TILE_BYTES + tcf::BMAT_BYTES;
 constexpr unsigned long long TC_MIN_PAIRS = 1ull << 14;  // smaller rounds are latency-bound: plain kernel
 
-template <int NPTS>
+// M = 0: any list of products (CSR).  M > 0: ONE product of M multiplicands with a deferred coefficient — the loops over products
+// and multiplicands are unrolled, so first / last / kdeg are compile-time and the per-pair control flow disappears.
+template <int NPTS, int M = 0>
 __global__ void __launch_bounds__(TC_THREADS, (NPTS >= SC_TC_WIDE_NPTS ? 2 : SC_TC_MIN_BLOCKS)) round_tc_kernel(const RoundParams p) {
     extern __shared__ __align__(1024) uint8_t tc_smem[];  // [TC_SLOTS] tiles, then the constants matrix
     __shared__ uint32_t s_red[32 * NPTS * 8];
@@ -108,34 +110,44 @@ __global__ void __launch_bounds__(TC_THREADS, (NPTS >= SC_TC_WIDE_NPTS ? 2 : SC_
     issue_mma(0);
 
     uint32_t q = 0;
+    // one work item: wait for its accumulator, read the two folded elements out of tensor memory, store them, multiply them in
+    auto item = [&](uint32_t k, uint32_t jj, bool first, bool last, uint32_t kdeg, unsigned long long b, Fr (&prod)[NPTS]) {
+        if (q + 1 < Q) issue_mma(q + 1);  // one item ahead: overlaps this item's arithmetic
+        const uint32_t a = q & 1u;
+        tcf::mbar_wait(&s_done[a], (q >> 1) & 1u);
+        tcf::tc_fence_after();
+        // the tile's shared-memory slot is free again (its MMAs completed): stage item q + TC_SLOTS into it
+        if (tma_q < Q) issue_tma();
+        uint32_t S[32];
+        tcf::tmem_ld32(lane_taddr + a * tcf::ACC_COLS, S);
+        tcf::tmem_ld_wait();
+        const Fr v0 = tcf::columns_to_fr(S);
+        tcf::tmem_ld32(lane_taddr + a * tcf::ACC_COLS + 32, S);
+        tcf::tmem_ld_wait();
+        tcf::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tcf::mbar_arrive(&s_empty[a]);
+        const Fr v1 = tcf::columns_to_fr(S);
+        if (p.write_fold && p.prod_first[jj]) {
+            uint32_t* dst = p.tab_out[p.prod_indices[jj]] + b * 16;
+            fr::store(dst, v0);
+            fr::store(dst + 8, v1);
+        }
+        RegAccs<NPTS> accs{accw};
+        consume_pair_acc<NPTS, false, 1, (M > 0)>(p, k, first, last, kdeg, v0, v1, prod, accs);  // these rounds always skip P(1)
+        q++;
+    };
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const unsigned long long b = (unsigned long long)tile * tcf::TILE_ROWS + tid;
-        for (uint32_t k = 0; k < p.n_products; k++) {
+        if (M > 0) {
             Fr prod[NPTS];
-            const uint32_t j0 = p.prod_offsets[k], j1 = p.prod_offsets[k + 1];
-            for (uint32_t jj = j0; jj < j1; jj++, q++) {
-                if (q + 1 < Q) issue_mma(q + 1);  // one item ahead: overlaps this item's arithmetic
-                const uint32_t a = q & 1u;
-                tcf::mbar_wait(&s_done[a], (q >> 1) & 1u);
-                tcf::tc_fence_after();
-                // the tile's shared-memory slot is free again (its MMAs completed): stage item q + TC_SLOTS into it
-                if (tma_q < Q) issue_tma();
-                uint32_t S[32];
-                tcf::tmem_ld32(lane_taddr + a * tcf::ACC_COLS, S);
-                tcf::tmem_ld_wait();
-                const Fr v0 = tcf::columns_to_fr(S);
-                tcf::tmem_ld32(lane_taddr + a * tcf::ACC_COLS + 32, S);
-                tcf::tmem_ld_wait();
-                tcf::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tcf::mbar_arrive(&s_empty[a]);
-                const Fr v1 = tcf::columns_to_fr(S);
-                if (p.write_fold && p.prod_first[jj]) {
-                    uint32_t* dst = p.tab_out[p.prod_indices[jj]] + b * 16;
-                    fr::store(dst, v0);
-                    fr::store(dst + 8, v1);
-                }
-                consume_pair<NPTS>(p, k, jj == j0, jj + 1 == j1, jj - j0 + 1, v0, v1, prod, accw);
+#pragma unroll
+            for (int jj = 0; jj < (M > 0 ? M : 1); jj++) item(0, (uint32_t)jj, jj == 0, jj + 1 == M, (uint32_t)jj + 1, b, prod);
+        } else {
+            for (uint32_t k = 0; k < p.n_products; k++) {
+                Fr prod[NPTS];
+                const uint32_t j0 = p.prod_offsets[k], j1 = p.prod_offsets[k + 1];
+                for (uint32_t jj = j0; jj < j1; jj++) item(k, jj, jj == j0, jj + 1 == j1, jj - j0 + 1, b, prod);
             }
         }
     }

@@ -19,7 +19,8 @@ constexpr uint32_t R1_TILE_ROWS = 64;                       // 128-byte rows (tw
 constexpr uint32_t R1_TILE_BYTES = R1_TILE_ROWS * 128;      // 8 KiB
 constexpr size_t R1_DYN_SMEM = (size_t)R1_SLOTS * R1_TILE_BYTES;
 
-template <int NPTS>
+// M as in round_tc_kernel: 0 = any list of products, M > 0 = one product of M multiplicands with a deferred coefficient (unrolled)
+template <int NPTS, int M = 0>
 __global__ void __launch_bounds__(R1_THREADS, (NPTS >= SC_R1_WIDE_NPTS ? 2 : 3)) round1_tma_kernel(const RoundParams p) {
     extern __shared__ __align__(1024) uint8_t r1_smem[];
     __shared__ uint32_t s_red[32 * NPTS * 8];
@@ -71,27 +72,36 @@ __global__ void __launch_bounds__(R1_THREADS, (NPTS >= SC_R1_WIDE_NPTS ? 2 : 3))
     for (uint32_t s = 0; s + 1 < R1_SLOTS && s < Q; s++) issue_tma();
 
     uint32_t q = 0;
+    auto item = [&](uint32_t k, bool first, bool last, uint32_t kdeg, Fr (&prod)[NPTS]) {
+        if (tma_q < Q) issue_tma();  // item q + R1_SLOTS - 1 into the slot item q - 1 used
+        const uint32_t slot = q % R1_SLOTS;
+        tcf::mbar_wait(&s_full[slot], (q / R1_SLOTS) & 1u);
+        const uint8_t* src = r1_smem + (size_t)slot * R1_TILE_BYTES + row_off;
+        Fr v0, v1;
+        {
+            const uint4 a = *reinterpret_cast<const uint4*>(src + (((4u * half + 0u) ^ sw) << 4));
+            const uint4 b = *reinterpret_cast<const uint4*>(src + (((4u * half + 1u) ^ sw) << 4));
+            const uint4 c = *reinterpret_cast<const uint4*>(src + (((4u * half + 2u) ^ sw) << 4));
+            const uint4 d = *reinterpret_cast<const uint4*>(src + (((4u * half + 3u) ^ sw) << 4));
+            v0.l[0] = a.x; v0.l[1] = a.y; v0.l[2] = a.z; v0.l[3] = a.w; v0.l[4] = b.x; v0.l[5] = b.y; v0.l[6] = b.z; v0.l[7] = b.w;
+            v1.l[0] = c.x; v1.l[1] = c.y; v1.l[2] = c.z; v1.l[3] = c.w; v1.l[4] = d.x; v1.l[5] = d.y; v1.l[6] = d.z; v1.l[7] = d.w;
+        }
+        __syncwarp();
+        if (lane == 0) tcf::mbar_arrive(&s_empty[slot]);
+        RegAccs<NPTS> accs{accw};
+        consume_pair_acc<NPTS, false, 0, (M > 0)>(p, k, first, last, kdeg, v0, v1, prod, accs);  // round 1 sums every point
+        q++;
+    };
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (uint32_t k = 0; k < p.n_products; k++) {
+        if (M > 0) {
             Fr prod[NPTS];
-            const uint32_t j0 = p.prod_offsets[k], j1 = p.prod_offsets[k + 1];
-            for (uint32_t jj = j0; jj < j1; jj++, q++) {
-                if (tma_q < Q) issue_tma();  // item q + R1_SLOTS - 1 into the slot item q - 1 used
-                const uint32_t slot = q % R1_SLOTS;
-                tcf::mbar_wait(&s_full[slot], (q / R1_SLOTS) & 1u);
-                const uint8_t* src = r1_smem + (size_t)slot * R1_TILE_BYTES + row_off;
-                Fr v0, v1;
-                {
-                    const uint4 a = *reinterpret_cast<const uint4*>(src + (((4u * half + 0u) ^ sw) << 4));
-                    const uint4 b = *reinterpret_cast<const uint4*>(src + (((4u * half + 1u) ^ sw) << 4));
-                    const uint4 c = *reinterpret_cast<const uint4*>(src + (((4u * half + 2u) ^ sw) << 4));
-                    const uint4 d = *reinterpret_cast<const uint4*>(src + (((4u * half + 3u) ^ sw) << 4));
-                    v0.l[0] = a.x; v0.l[1] = a.y; v0.l[2] = a.z; v0.l[3] = a.w; v0.l[4] = b.x; v0.l[5] = b.y; v0.l[6] = b.z; v0.l[7] = b.w;
-                    v1.l[0] = c.x; v1.l[1] = c.y; v1.l[2] = c.z; v1.l[3] = c.w; v1.l[4] = d.x; v1.l[5] = d.y; v1.l[6] = d.z; v1.l[7] = d.w;
-                }
-                __syncwarp();
-                if (lane == 0) tcf::mbar_arrive(&s_empty[slot]);
-                consume_pair<NPTS>(p, k, jj == j0, jj + 1 == j1, jj - j0 + 1, v0, v1, prod, accw);
+#pragma unroll
+            for (int jj = 0; jj < (M > 0 ? M : 1); jj++) item(0, jj == 0, jj + 1 == M, (uint32_t)jj + 1, prod);
+        } else {
+            for (uint32_t k = 0; k < p.n_products; k++) {
+                Fr prod[NPTS];
+                const uint32_t j0 = p.prod_offsets[k], j1 = p.prod_offsets[k + 1];
+                for (uint32_t jj = j0; jj < j1; jj++) item(k, jj == j0, jj + 1 == j1, jj - j0 + 1, prod);
             }
         }
     }
