@@ -148,6 +148,55 @@ inline const std::vector<F>& lagrange_weights(uint32_t d) {
     return w;
 }
 
+// Alternative evaluation points -> the message P(0..d) (kernels.cuh consume_pair_acc ALT).  The device sums the product
+// polynomial at the finite points F_d = the first d of (0, 1, -1, 2, -2) and delivers c_d, the coefficient of t^d ("the point
+// at infinity").  R(t) = P(t) - c_d t^d has degree < d and is known on the d points of F_d, so
+//     P(t) = sum_f L_f(t) R(f) + c_d t^d,    L_f(t) = prod_{g != f} (t - g) / (f - g)
+// for t = 0..d — exact field arithmetic, hence the element the reference computes.  fin[i] = P(F_d[i]).  d <= 5.
+inline F from_i64(long long k) {
+    return k >= 0 ? from_u64((uint64_t)k) : sub(F{{0, 0, 0, 0}}, from_u64((uint64_t)(-k)));
+}
+inline void alt_to_standard(uint32_t d, const F* fin, const F& cd, F* out) {
+    static const long long NODES[5] = {0, 1, -1, 2, -2};
+    static std::vector<F> cache[6];  // [d]: (d+1) x d basis values L_f(t), then (d+1) powers t^d
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        std::vector<F>& m = cache[d];
+        if (m.empty()) {
+            std::vector<F> fresh((size_t)(d + 1) * d + (d + 1));
+            for (uint32_t t = 0; t <= d; t++) {
+                for (uint32_t f = 0; f < d; f++) {
+                    F num = ONE, den = ONE;
+                    for (uint32_t g = 0; g < d; g++) {
+                        if (g == f) continue;
+                        num = mul(num, from_i64((long long)t - NODES[g]));
+                        den = mul(den, from_i64(NODES[f] - NODES[g]));
+                    }
+                    fresh[(size_t)t * d + f] = mul(num, inverse(den));
+                }
+                F pw = ONE;
+                for (uint32_t e = 0; e < d; e++) pw = mul(pw, from_u64(t));
+                fresh[(size_t)(d + 1) * d + t] = pw;
+            }
+            m.swap(fresh);
+        }
+    }
+    const std::vector<F>& m = cache[d];
+    F r[5];
+    for (uint32_t f = 0; f < d; f++) {  // R(f) = P(f) - c_d f^d
+        F pw = ONE;
+        const F node = from_i64(NODES[f]);
+        for (uint32_t e = 0; e < d; e++) pw = mul(pw, node);
+        r[f] = sub(fin[f], mul(cd, pw));
+    }
+    for (uint32_t t = 0; t <= d; t++) {
+        F acc = mul(cd, m[(size_t)(d + 1) * d + t]);
+        for (uint32_t f = 0; f < d; f++) acc = add(acc, mul(m[(size_t)t * d + f], r[f]));
+        out[t] = acc;
+    }
+}
+
 // The value at r of the degree-d polynomial through (j, evals[j]), j = 0..d (interpolate_uni_poly, verifier.rs:139).
 inline F interpolate(const F* evals, uint32_t d, const F& r) {
     const std::vector<F>& w = lagrange_weights(d);

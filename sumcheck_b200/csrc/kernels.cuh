@@ -181,24 +181,104 @@ struct RegAccs {
 };
 // ... or parked in tensor memory (tma_round1.cuh TmemAccs): same interface.
 
-// SKIP: -1 = p.skip1 decides at run time, 0 / 1 = known when the kernel is built (round 1 never skips P(1), the tensor-core fold
-// rounds always do).  SIMPLE: ONE product whose coefficient is deferred to the end of the round and a single launch per round
-// (t0 == 0) — then nothing about the coefficient or the first evaluation point is left to decide per pair.  With compile-time
-// first / last / kdeg (callers that unroll over the multiplicands of a single product) the whole body is branch-free.
-template <int NPTS, bool ILP = false, int SKIP = -1, bool SIMPLE = false, class ACCS>
-__device__ __forceinline__ void consume_pair_acc(const RoundParams& p, uint32_t k, bool first, bool last, uint32_t kdeg, const Fr& v0,
-                                                 const Fr& v1, Fr (&prod)[NPTS], ACCS& accs) {
+// SKIP: -1 = p.skip1 decides at run time, 0 / 1 = known when the kernel is built (round 1 never skips P(1), the fold rounds of
+// a single launch always do).  SIMPLE: ONE product whose coefficient is deferred to the end of the round and a single launch per
+// round (t0 == 0) — then nothing about the coefficient or the first evaluation point is left to decide per pair.
+//
+// ALT (needs SKIP known): the sums are taken at the points  0, 1, inf, -1, 2, -2  (round 1: the first d+1 of them; rounds that
+// skip P(1): the same list without the 1) instead of 0, 1, 2, .., d.  "inf" is the coefficient of t^d, i.e. the product of the
+// STEPS table[2b+1] - table[2b].  On these points a multiplicand's values cost at most ONE modular add each —
+//     v(0) = table[2b]   v(1) = table[2b+1]   v(inf) = step   v(-1) = v(0) - step   v(2) = v(1) + step   v(-2) = v(-1) - step
+// — where the consecutive points cost one add per point including t = 1 (4 instead of 2 add/sub per table at degree 3).  The host
+// recovers P(0..d) exactly (host_fr.h alt_to_standard: interpolation of P(t) - c_d t^d through the d finite points), so the
+// message is bit-identical.  `full`: the product has exactly `degree` multiplicands; a shorter one has no t^d term, so it is left
+// out of the inf slot.
+__device__ __forceinline__ int point_index(bool skip1, int s) { return skip1 ? (s == 0 ? 0 : s + 1) : s; }  // into 0, 1, inf, -1, 2, -2
+
+template <int NPTS, bool ILP = false, int SKIP = -1, bool SIMPLE = false, bool ALT = false, class ACCS>
+__device__ __forceinline__ void consume_pair_acc(const RoundParams& p, uint32_t k, bool first, bool last, uint32_t kdeg, bool full,
+                                                 const Fr& v0, const Fr& v1, Fr (&prod)[NPTS], ACCS& accs) {
+    static_assert(!ALT || SKIP >= 0, "the alternative points need a compile-time skip flag");
     const bool skip1 = SKIP < 0 ? (p.skip1 != 0) : (SKIP != 0);
     // prover.rs:119-124: start = table[2b], step = table[2b+1] - start; product[t] *= start; start += step
     Fr step = fr::sub(v1, v0);
-    Fr cur = v0;
+    Fr cur = v0, one = v1;  // the multiplicand at t = 0 and t = 1 (ALT)
     if (!SIMPLE) {
         for (uint32_t s = 0; s < p.t0; s++) cur = fr::add(cur, step);  // only for d+1 > MAX_NPTS
         if (first && !p.defer_coeff && !(p.prod_scaled && p.prod_scaled[k])) {  // c_k * prod_j(...): scale the first multiplicand's line once
             Fr c = fr::load(p.coeffs + 8 * k);
             cur = fr::mul(cur, c);
             step = fr::mul(step, c);
+            if (ALT) one = fr::add(cur, step);
         }
+    }
+    if (ALT) {
+        // value of this multiplicand at the point of slot t (each visited once, in slot order: -1 before -2)
+        Fr vm1 = cur;
+#define SC_ALT_VALUE(t, out)                                                          \
+        {                                                                             \
+            const int pi_ = point_index(skip1, (t));                                  \
+            if (pi_ == 0) out = cur;                                                  \
+            else if (pi_ == 1) out = one;                                             \
+            else if (pi_ == 2) out = step;                                            \
+            else if (pi_ == 3) { vm1 = fr::sub(cur, step); out = vm1; }               \
+            else if (pi_ == 4) out = fr::add(one, step);                              \
+            else { vm1 = fr::sub(vm1, step); out = vm1; }                             \
+        }
+        if (first && last) {
+            accs.begin();
+#pragma unroll
+            for (int t = 0; t < NPTS; t++) {
+                Fr v;
+                SC_ALT_VALUE(t, v)
+                if (point_index(skip1, t) == 2 && !full) continue;
+                accs.add_shifted(t, v);
+            }
+        } else if (first) {
+#pragma unroll
+            for (int t = 0; t < NPTS; t++) SC_ALT_VALUE(t, prod[t])
+        } else if (last) {
+            accs.begin();
+#pragma unroll
+            for (int t = 0; t < NPTS; t++) {
+                Fr v;
+                SC_ALT_VALUE(t, v)
+                if (point_index(skip1, t) == 2 && !full) continue;
+                accs.mac(t, prod[t], v);
+            }
+        } else if (ILP) {
+            fr::FrN<NPTS> a, b;
+#pragma unroll
+            for (int t = 0; t < NPTS; t++) {
+                a.v[t] = prod[t];
+                SC_ALT_VALUE(t, b.v[t])
+            }
+            const fr::FrN<NPTS> r = fr::mul_lazy_n<NPTS>(a, b);
+#pragma unroll
+            for (int t = 0; t < NPTS; t++) prod[t] = r.v[t];
+        } else {
+            // After two multiplicands the running product q is quadratic in the evaluation point: from q(0), q(1), q(inf)
+            //   q(-1) = 2 q(0) - q(1) + 2 q(inf)        q(2) = 2 q(1) - q(0) + 2 q(inf)
+            // (exact), so round 1 multiplies three points of the second multiplicand and derives the others.
+            const bool derive = !skip1 && kdeg == 2;
+#pragma unroll
+            for (int t = 0; t < NPTS; t++) {
+                if (derive && t == 3) {
+                    const Fr i2 = fr::add(prod[2], prod[2]);
+                    prod[3] = fr::add(fr::sub(fr::add(prod[0], prod[0]), prod[1]), i2);
+                } else if (derive && t == 4) {
+                    const Fr i2 = fr::add(prod[2], prod[2]);
+                    prod[4] = fr::add(fr::sub(fr::add(prod[1], prod[1]), prod[0]), i2);
+                } else {
+                    Fr v;
+                    SC_ALT_VALUE(t, v)
+                    // round 1 derives points from these products (canonical needed); the fold rounds only multiply them again
+                    prod[t] = skip1 ? fr::mul_lazy(prod[t], v) : fr::mul(prod[t], v);
+                }
+            }
+        }
+#undef SC_ALT_VALUE
+        return;
     }
     // slot s holds evaluation point t0+s, or with skip1 the points 0, 2, 3, ..: one extra step after slot 0
 #define SC_NEXT_POINT(t)                                        \
@@ -270,14 +350,15 @@ __device__ __forceinline__ void consume_pair_acc(const RoundParams& p, uint32_t 
 #undef SC_NEXT_POINT
 }
 
-template <int NPTS, bool ILP = false>
-__device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, bool first, bool last, uint32_t kdeg, const Fr& v0,
+template <int NPTS, bool ILP = false, bool ALT = false>
+__device__ __forceinline__ void consume_pair(const RoundParams& p, uint32_t k, bool first, bool last, uint32_t kdeg, bool full, const Fr& v0,
                                              const Fr& v1, Fr (&prod)[NPTS], fr::WideAcc (&accw)[NPTS]) {
     RegAccs<NPTS> accs{accw};
-    consume_pair_acc<NPTS, ILP>(p, k, first, last, kdeg, v0, v1, prod, accs);
+    // ALT is only used by the resident kernel, whose rounds always fold and skip P(1)
+    consume_pair_acc<NPTS, ILP, ALT ? 1 : -1, false, ALT>(p, k, first, last, kdeg, full, v0, v1, prod, accs);
 }
 
-template <int NPTS, bool FOLD, bool STREAM, bool ILP = false>
+template <int NPTS, bool FOLD, bool STREAM, bool ILP = false, bool ALT = false>
 __device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const uint32_t* foldC, unsigned long long b0,
                                                  unsigned long long stride, fr::WideAcc (&accw)[NPTS]) {
     for (unsigned long long b = b0; b < p.n_pairs; b += stride) {
@@ -314,7 +395,7 @@ __device__ __forceinline__ void accumulate_pairs(const RoundParams& p, const uin
                     v0 = fr::load_stream(src);
                     v1 = fr::load_stream(src + 8);
                 }
-                consume_pair<NPTS, ILP>(p, k, jj == j0, jj + 1 == j1, jj - j0 + 1, v0, v1, prod, accw);
+                consume_pair<NPTS, ILP, ALT>(p, k, jj == j0, jj + 1 == j1, jj - j0 + 1, j1 - j0 == p.degree, v0, v1, prod, accw);
             }
         }
     }
@@ -351,10 +432,11 @@ __device__ __forceinline__ void accumulate_fine(const RoundParams& p, const uint
     if (live && u < p.n_products * NPTS) {  // phase B
         const uint32_t k = u / NPTS, s = u % NPTS;
         my_pt = (int)s;
-        const uint32_t steps = p.skip1 ? (s == 0 ? 0u : s + 1u) : p.t0 + s;  // the evaluation point of slot s
+        const int pi = point_index(true, (int)s);  // the resident rounds skip P(1): points 0, inf, -1, 2, -2 (consume_pair_acc ALT)
         const uint32_t j0 = p.prod_offsets[k], j1 = p.prod_offsets[k + 1];
+        if (pi == 2 && j1 - j0 != p.degree) my_pt = -1;  // a product shorter than the degree has no t^d term
         Fr prod = fr::zero();
-        for (uint32_t jj = j0; jj < j1; jj++) {
+        for (uint32_t jj = j0; jj < j1 && my_pt >= 0; jj++) {
             Fr v0, v1;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
@@ -362,8 +444,12 @@ __device__ __forceinline__ void accumulate_fine(const RoundParams& p, const uint
                 v1.l[i] = slots[(base + 2 * jj + 1) * 8 + i];
             }
             const Fr step = fr::sub(v1, v0);
-            Fr cur = v0;
-            for (uint32_t a = 0; a < steps; a++) cur = fr::add(cur, step);
+            Fr cur;
+            if (pi == 0) cur = v0;
+            else if (pi == 2) cur = step;
+            else if (pi == 3) cur = fr::sub(v0, step);
+            else if (pi == 4) cur = fr::add(v1, step);
+            else cur = fr::sub(fr::sub(v0, step), step);
             const bool first = jj == j0, last = jj + 1 == j1;
             if (first && !p.defer_coeff && !(p.prod_scaled && p.prod_scaled[k])) cur = fr::mul(cur, fr::load(p.coeffs + 8 * k));
             if (first && last) fr::wide_add_shifted(acc, cur);

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(RES_THREADS, 2) resident_kernel(const Resident
         } else {
 #pragma unroll
             for (int t = 0; t < NPTS; t++) fr::wide_zero(accw[t]);
-            accumulate_pairs<NPTS, true, false, true>(p, s_foldC, (unsigned long long)c * RES_THREADS + tid, (unsigned long long)n_act * RES_THREADS, accw);
+            accumulate_pairs<NPTS, true, false, true, true>(p, s_foldC, (unsigned long long)c * RES_THREADS + tid, (unsigned long long)n_act * RES_THREADS, accw);
             __threadfence();  // this thread's folded-table stores are visible GPU-wide before the CTA reports its arrival
             tk2 = clock64();
             block_sum_wide<NPTS>(accw, s_part, s_tot, s_out, n_act == 1);  // the CTA's sums as NPTS 17-limb integers (no Montgomery reduction)

@@ -257,6 +257,7 @@ struct sc_prover {
     bool used_skip1 = false;  // last device round summed t = 0, 2, .., d only
     // host_post: rounds deliver only their raw sums; coefficient, claim and canonical forms are finished on the host
     bool host_post = false, raw_active = false;
+    bool alt_active = false;  // the raw sums just delivered are at the alternative points 0, 1, inf, -1, 2, -2 (kernels.cuh ALT)
     // Pipelined upload (sc_prover_load_tables): the tables arrive in EAGER_CHUNKS pieces on a copy stream while round 1 —
     // which needs no challenge — is summed piece by piece behind them; the first prove_round then only adds the pieces up.
     bool eager_valid = false;
@@ -456,6 +457,7 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
         rp.seq = ++p->seq;
     }
     p->raw_active = false;
+    p->alt_active = false;
     if (fold && p->d <= (uint32_t)sck::MAX_NPTS && p->d_lagrange) {
         // rounds >= 2: P(0) + P(1) = P_prev(r) (the verifier's check, verifier.rs:109), so only t = 0, 2, .., d are summed
         rp.skip1 = 1;
@@ -469,8 +471,10 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
             p->raw_npts = p->d;
         }
         cudaError_t e;
-        if (p->tc_buf_ok[p->cur] && rp.n_pairs >= p->tc_min_pairs) {
-            // large fold round: tables staged by TMA, fix_variables on the tensor cores (tc_round.cuh)
+        if (p->tc_buf_ok[p->cur] && rp.n_pairs >= p->tc_min_pairs && rp.raw_out) {
+            // large fold round: tables staged by TMA, fix_variables on the tensor cores (tc_round.cuh).  These kernels sum
+            // at the alternative points, which only the host finishing converts back (raw delivery)
+            p->alt_active = true;
             rp.tmaps = p->d_maps + (size_t)p->cur * p->T * sizeof(CUtensorMap);
             p->launches++;
             p->tc_rounds++;
@@ -506,7 +510,8 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
             p->raw_npts = take;
         }
         cudaError_t e;
-        if (!fold && p->r1_ok && p->cur == 0 && take == p->d + 1 && rp.n_pairs >= p->tc_min_pairs) {
+        if (!fold && p->r1_ok && p->cur == 0 && take == p->d + 1 && rp.n_pairs >= p->tc_min_pairs && rp.raw_out) {
+            p->alt_active = true;  // round1_tma_kernel sums at the alternative points (raw delivery only)
             rp.tmaps = p->d_maps + (size_t)3 * p->T * sizeof(CUtensorMap);  // round 1, one launch: TMA-staged kernel
             switch (take) {
                 case 1: e = launch_round1_tma<1>(p, rp); break;
@@ -901,7 +906,25 @@ void host_finish_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
     const bool scale = p->n_products == 1;
     if (scale) memcpy(&coeff, p->h_coeffs.data(), 32);
     auto fin = [&](const hfr::F& x) { return scale ? hfr::mul(x, coeff) : x; };
-    if (w->used_skip1) {  // sums hold P(0), P(2), .., P(d)
+    if (w->alt_active && d >= 2) {
+        // sums at the alternative points: round 1 slots = (0, 1, inf, -1, 2)[0..d]; a round that skipped P(1): (0, inf, -1, 2, -2)[0..d-1]
+        hfr::F at[5], cd;  // at[i] = P at the i-th of (0, 1, -1, 2, -2)
+        if (w->used_skip1) {
+            hfr::F rr, prev[8];
+            memcpy(&rr, r, 32);
+            memcpy(prev, p->h_prev.data(), (size_t)(d + 1) * 32);
+            at[0] = fin(sums[0]);
+            at[1] = hfr::sub(hfr::interpolate(prev, d, rr), at[0]);  // P(1) = P_prev(r) - P(0) (verifier.rs:109)
+            cd = fin(sums[1]);
+            for (uint32_t i = 2; i < d; i++) at[i] = fin(sums[i]);
+        } else {
+            at[0] = fin(sums[0]);
+            at[1] = fin(sums[1]);
+            cd = fin(sums[2]);
+            for (uint32_t i = 2; i < d; i++) at[i] = fin(sums[i + 1]);
+        }
+        hfr::alt_to_standard(d, at, cd, out);
+    } else if (w->used_skip1) {  // sums hold P(0), P(2), .., P(d)
         hfr::F rr, prev[8];
         memcpy(&rr, r, 32);
         memcpy(prev, p->h_prev.data(), (size_t)(d + 1) * 32);
@@ -1085,6 +1108,7 @@ int resident_collect(sc_prover* p, sc_prover* w, const uint64_t* r) {
     }
     w->raw_npts = d;
     w->used_skip1 = true;
+    w->alt_active = true;  // the resident kernel sums at the alternative points
     host_finish_round(p, w, r);
     memcpy(p->h_prev.data(), p->h_evals, (size_t)(d + 1) * 32);
     w->cur = (w->cur == 1) ? 2 : 1;
@@ -1158,6 +1182,7 @@ int prove_round_issue(sc_prover* p, const uint64_t* r_or_null) {
         memcpy(p->h_result, tot, (size_t)npts * 32);
         p->raw_npts = npts;
         p->used_skip1 = false;
+        p->alt_active = true;  // the chunks were summed by round1_tma_kernel
         host_finish_round(p, p, nullptr);
         memcpy(p->h_prev.data(), p->h_evals, (size_t)npts * 32);
         p->out_evals = p->d_evals;

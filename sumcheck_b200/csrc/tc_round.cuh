@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(TC_THREADS, (NPTS >= SC_TC_WIDE_NPTS ? 2 : SC_
 
     uint32_t q = 0;
     // one work item: wait for its accumulator, read the two folded elements out of tensor memory, store them, multiply them in
-    auto item = [&](uint32_t k, uint32_t jj, bool first, bool last, uint32_t kdeg, unsigned long long b, Fr (&prod)[NPTS]) {
+    auto item = [&](uint32_t k, uint32_t jj, bool first, bool last, uint32_t kdeg, bool full, unsigned long long b, Fr (&prod)[NPTS]) {
         if (q + 1 < Q) issue_mma(q + 1);  // one item ahead: overlaps this item's arithmetic
         const uint32_t a = q & 1u;
         tcf::mbar_wait(&s_done[a], (q >> 1) & 1u);
@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(TC_THREADS, (NPTS >= SC_TC_WIDE_NPTS ? 2 : SC_
             fr::store(dst + 8, v1);
         }
         RegAccs<NPTS> accs{accw};
-        consume_pair_acc<NPTS, false, 1, (M > 0)>(p, k, first, last, kdeg, v0, v1, prod, accs);  // these rounds always skip P(1)
+        // these rounds always skip P(1) and deliver raw sums to the host: alternative points (kernels.cuh consume_pair_acc)
+        consume_pair_acc<NPTS, false, 1, (M > 0), true>(p, k, first, last, kdeg, full, v0, v1, prod, accs);
         q++;
     };
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -142,12 +143,12 @@ __global__ void __launch_bounds__(TC_THREADS, (NPTS >= SC_TC_WIDE_NPTS ? 2 : SC_
         if (M > 0) {
             Fr prod[NPTS];
 #pragma unroll
-            for (int jj = 0; jj < (M > 0 ? M : 1); jj++) item(0, (uint32_t)jj, jj == 0, jj + 1 == M, (uint32_t)jj + 1, b, prod);
+            for (int jj = 0; jj < (M > 0 ? M : 1); jj++) item(0, (uint32_t)jj, jj == 0, jj + 1 == M, (uint32_t)jj + 1, true, b, prod);
         } else {
             for (uint32_t k = 0; k < p.n_products; k++) {
                 Fr prod[NPTS];
                 const uint32_t j0 = p.prod_offsets[k], j1 = p.prod_offsets[k + 1];
-                for (uint32_t jj = j0; jj < j1; jj++) item(k, jj, jj == j0, jj + 1 == j1, jj - j0 + 1, b, prod);
+                for (uint32_t jj = j0; jj < j1; jj++) item(k, jj, jj == j0, jj + 1 == j1, jj - j0 + 1, j1 - j0 == p.degree, b, prod);
             }
         }
     }

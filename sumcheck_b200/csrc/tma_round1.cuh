@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(R1_THREADS, (NPTS >= SC_R1_WIDE_NPTS ? 2 : 3))
     for (uint32_t s = 0; s + 1 < R1_SLOTS && s < Q; s++) issue_tma();
 
     uint32_t q = 0;
-    auto item = [&](uint32_t k, bool first, bool last, uint32_t kdeg, Fr (&prod)[NPTS]) {
+    auto item = [&](uint32_t k, bool first, bool last, uint32_t kdeg, bool full, Fr (&prod)[NPTS]) {
         if (tma_q < Q) issue_tma();  // item q + R1_SLOTS - 1 into the slot item q - 1 used
         const uint32_t slot = q % R1_SLOTS;
         tcf::mbar_wait(&s_full[slot], (q / R1_SLOTS) & 1u);
@@ -89,19 +89,20 @@ __global__ void __launch_bounds__(R1_THREADS, (NPTS >= SC_R1_WIDE_NPTS ? 2 : 3))
         __syncwarp();
         if (lane == 0) tcf::mbar_arrive(&s_empty[slot]);
         RegAccs<NPTS> accs{accw};
-        consume_pair_acc<NPTS, false, 0, (M > 0)>(p, k, first, last, kdeg, v0, v1, prod, accs);  // round 1 sums every point
+        // round 1 sums d+1 points and delivers raw sums to the host: alternative points 0, 1, inf, -1, 2 (kernels.cuh consume_pair_acc)
+        consume_pair_acc<NPTS, false, 0, (M > 0), true>(p, k, first, last, kdeg, full, v0, v1, prod, accs);
         q++;
     };
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (M > 0) {
             Fr prod[NPTS];
 #pragma unroll
-            for (int jj = 0; jj < (M > 0 ? M : 1); jj++) item(0, jj == 0, jj + 1 == M, (uint32_t)jj + 1, prod);
+            for (int jj = 0; jj < (M > 0 ? M : 1); jj++) item(0, jj == 0, jj + 1 == M, (uint32_t)jj + 1, true, prod);
         } else {
             for (uint32_t k = 0; k < p.n_products; k++) {
                 Fr prod[NPTS];
                 const uint32_t j0 = p.prod_offsets[k], j1 = p.prod_offsets[k + 1];
-                for (uint32_t jj = j0; jj < j1; jj++) item(k, jj == j0, jj + 1 == j1, jj - j0 + 1, prod);
+                for (uint32_t jj = j0; jj < j1; jj++) item(k, jj == j0, jj + 1 == j1, jj - j0 + 1, j1 - j0 == p.degree, prod);
             }
         }
     }
