@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
-"""usage: ncu_summary.py <report.ncu-rep>: key metrics + warp-stall breakdown per profiled launch (reads the raw page)."""
+"""usage: ncu_summary.py <report.ncu-rep | raw-page.csv>: key metrics + warp-stall breakdown per profiled launch (reads the raw page)."""
 import csv, subprocess, sys
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = open(sys.argv[1]).read() if sys.argv[1].endswith('.csv') else \
+    subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h = rows[0]
 keys = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__registers_per_thread',
