@@ -276,6 +276,10 @@ class ProverState:
         """Rounds served by the resident kernel (one cooperative launch for all small rounds) since creation/reset."""
         return int(capi.lib().sc_prover_resident_round_count(self._h))
 
+    def gemm_round_count(self):
+        """Rounds that ran on the tensor-core contraction kernels (degree-3 products) since creation/reset."""
+        return int(capi.lib().sc_prover_gemm_round_count(self._h))
+
     def tc_round_count(self):
         """Fold rounds that ran on the TMA + tensor-core kernel since creation/reset."""
         return int(capi.lib().sc_prover_tc_round_count(self._h))

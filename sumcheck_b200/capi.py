@@ -51,6 +51,7 @@ SIGNATURES = {
     "sc_prover_launch_count": (C.c_uint64, [C.c_void_p]),
     "sc_prover_tc_round_count": (C.c_uint64, [C.c_void_p]),
     "sc_prover_resident_round_count": (C.c_uint64, [C.c_void_p]),
+    "sc_prover_gemm_round_count": (C.c_uint64, [C.c_void_p]),
     "sc_release_cached_memory": (None, []),
     "sc_fr_interpolate": (C.c_int, [U64P, C.c_uint32, U64P, U64P]),
     "sc_poly_evaluate": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, U64P, U32P, U32P, U64P, C.c_int, U64P]),

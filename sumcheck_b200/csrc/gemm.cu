@@ -1,0 +1,71 @@
+// Translation unit of the tensor-core contraction kernels (gemm_sum.cuh): launchers only.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "gemm_sum.cuh"
+
+namespace gsum {
+
+cudaError_t init_constants() { return fr::fr_init_constants(); }  // this TU's copy of the __constant__ modulus
+
+#ifndef SC_GEMM_G1
+#define SC_GEMM_G1 4  // compute groups per CTA, round 1
+#endif
+#ifndef SC_GEMM_GF
+#define SC_GEMM_GF 3  // compute groups per CTA, fold rounds (shared memory and tensor memory allow three)
+#endif
+constexpr int G1 = SC_GEMM_G1, GF = SC_GEMM_GF;
+
+int groups_round1() { return G1; }
+int groups_fold() { return GF; }
+
+// TAG: one instantiation (and one set of per-device flags) per kernel — the kernels share a function-pointer type
+template <int TAG, class K>
+static cudaError_t prepare(K kernel, size_t smem) {
+    static bool ready_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (ready_dev[dev]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    if (getenv("SC_DEBUG")) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess)
+            fprintf(stderr, "gemm kernel: %d registers, %zu B static + %zu B dynamic shared memory\n", fa.numRegs, fa.sharedSizeBytes, smem);
+    }
+    ready_dev[dev] = true;
+    return cudaSuccess;
+}
+
+// grid: one CTA per SM, never more CTAs than there are items for their first groups
+static int grid_for(uint32_t items, int G, int sms) {
+    const uint32_t need = (items + G - 1) / G;
+    return (int)(need < (uint32_t)sms ? need : (uint32_t)sms);
+}
+
+// items a single launch may carry (every CTA at most MAX_ITEMS_PER_CTA per group)
+unsigned long long max_items_round1(int sms) { return (unsigned long long)sms * G1 * MAX_ITEMS_PER_CTA; }
+unsigned long long max_items_fold(int sms) { return (unsigned long long)sms * GF * MAX_ITEMS_PER_CTA; }
+
+cudaError_t launch_round1(const Params& P, int sms, cudaStream_t stream) {
+    const size_t smem = R1Smem<G1>::BYTES;
+    cudaError_t e = prepare<1>(gemm_round1_kernel<G1>, smem);
+    if (e != cudaSuccess) return e;
+    gemm_round1_kernel<G1><<<grid_for(P.items, G1, sms), G1 * 128 + 64, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fold(const Params& P, int sms, cudaStream_t stream) {
+    const size_t smem = FoldSmem<GF>::BYTES;
+    cudaError_t e = prepare<2>(gemm_fold_kernel<GF>, smem);
+    if (e != cudaSuccess) return e;
+    gemm_fold_kernel<GF><<<grid_for(P.items, GF, sms), GF * 128 + 64, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace gsum

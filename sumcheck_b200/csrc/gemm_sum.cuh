@@ -1,0 +1,546 @@
+// The multiply-reduce of prove_round as a tensor-core contraction (sm_100a, tcgen05.mma.kind::i8).
+//
+// prover.rs:110-148 sums, over all pairs b of the hypercube, the product of the multiplicands' evaluation lines.  For a product
+// of three tables that is  P(t) = sum_b q_b(t) * A2_b(t),  q_b(t) = A0_b(t) * A1_b(t).  Only q_b needs per-pair multiplications;
+// the OUTER sum is a contraction over b, and over the BYTES of the two factors
+//     sum_b x_b * y_b = sum_{u,v} 2^(8(u+v)) * sum_b x_b[u] * y_b[v]
+// it is a u8 x u8 -> s32 matrix product with the pair index as the K dimension:  D = X^T Y,  X = [pairs][bytes of x],
+// Y = [pairs][bytes of y] — exactly what tcgen05.mma computes (both operands MN-major: the bytes of one pair are contiguous).
+// So a thread only has to produce, per pair, three PLAIN 256 x 256-bit products of table values
+//     q0 = a0*a1,   q1 = b0*b1,   qs = (a0+b0)*(a1+b1)             (a_j = table_j[2b], b_j = table_j[2b+1]; Karatsuba: qs-q0-q1
+// is the middle coefficient of q_b(t)) as 64-byte integers in shared memory — no Montgomery reduction, no modular add, no lazy
+// accumulator — and the tensor core multiplies them with the 64 bytes [a2 | b2] of the third table and sums over the pairs.
+// The six sums  Z[i][j] = sum_b q_i * y_j  (i in {q0, q1, qs}, y in {a2, b2}) determine P completely:
+//     P(t) = sum_ij wX_i(t) wY_j(t) Z[i][j],   wX = ((1-t)(1-2t), t(2t-1), t(1-t)),   wY = (1-t, t)
+// which the host evaluates at t = 0..d after reducing the six big integers mod p (host_fr.h gemm_finish) — all exact, so the
+// message is bit-identical to the reference's.  Per pair at degree 3: 192 IMAD.WIDE instead of 589 (round 1) / 573 (fold rounds).
+//
+// Kernel shape: ONE persistent CTA per SM = G compute groups of 128 threads (a group owns one 128-pair tile at a time) + two
+// producer warps.  Warp P0 stages tables with TMA and, in fold rounds, issues the fix_variables MMAs (tc_fold.cuh) into
+// per-group accumulators; warp P1 issues the contraction MMAs of every group into ONE accumulator set in tensor memory (a
+// single issuing thread keeps the accumulating MMAs ordered).  After its last tile a CTA adds the anti-diagonals of D
+// (sum over u+v = k) into 64-bit totals in global memory; the last CTA carries them into the six integers and publishes.
+#pragma once
+#include "kernels.cuh"
+#include "tc_fold.cuh"
+
+namespace gsum {
+
+using fr::Fr;
+
+constexpr uint32_t TILE = 128;               // pairs per work item = threads per compute group
+constexpr uint32_t OUT_SLOT_WORDS = 512;     // mapped result slot: NB * OUT_LIMBS words, sequence flag in the last word
+constexpr uint32_t MAX_ITEMS_PER_CTA = 256;  // 4 K-steps of 32 pairs each: every s32 accumulator stays below 2^31
+constexpr uint32_t TOT_STRIDE = 128;         // u64 totals per block pair (>= number of anti-diagonals)
+
+struct Params {
+    sck::RoundParams rp;          // tables, CSR, tmaps (fold rounds: 128-byte rows), n_pairs, tile_base, host_out/host_flag/seq, counter, r
+    const void* ymaps;            // round 1: [n_tables] CUtensorMap with 64-byte rows (one pair), SWIZZLE_64B, 128-row boxes
+    unsigned long long* totals;   // [NB][TOT_STRIDE], zero before the launch; the publishing launch leaves it zero again
+    uint32_t publish;             // 0: only add into totals (a round split over several launches), 1: the last CTA publishes
+    uint32_t items;               // work items (tile, product) of this launch
+};
+
+// ---- MN-major operand descriptors (checked by tools/microbench/gemmsum.cu) ------------------------------------------------------
+// [k = pair][bytes] with the bytes of a pair contiguous: 128-byte rows + SWIZZLE_128B (layout type 2, 8-row groups 1024 B apart)
+// or 64-byte rows + SWIZZLE_64B (layout type 4, 8-row groups 512 B apart).  K = 32 pairs per instruction.
+__device__ __forceinline__ uint64_t mn_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)layout_type << 61);
+}
+// c_format S32 @4, a/b U8, a_major = b_major = MN @15/@16, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t idesc_u8_mn(uint32_t M, uint32_t N) {
+    return (2u << 4) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// ---- per-pair arithmetic ------------------------------------------------------------------------------------------------------
+// o = a * b as a plain 512-bit integer (64 IMAD.WIDE + the merge of the even/odd accumulators)
+__device__ __forceinline__ void mul_plain(const Fr& a, const Fr& b, uint32_t (&o)[16]) {
+    uint32_t ev[16], od[16], c0;
+    fr::mul_wide_eo(ev, od, a.l, b.l);
+    o[0] = ev[0];
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;\n\t"
+        : "=r"(o[1]), "=r"(o[2]), "=r"(o[3]), "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]), "=r"(c0)
+        : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(ev[8]), "r"(od[0]), "r"(od[1]), "r"(od[2]),
+          "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]));
+    asm("{ .reg .u32 t_; add.cc.u32 t_, %21, 0xffffffff; }\n\t"
+        "addc.cc.u32 %0, %7, %14;\n\t"
+        "addc.cc.u32 %1, %8, %15;\n\t"
+        "addc.cc.u32 %2, %9, %16;\n\t"
+        "addc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\t"
+        "addc.cc.u32 %5, %12, %19;\n\t"
+        "addc.u32 %6, %13, %20;\n\t"
+        : "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15])
+        : "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]), "r"(od[8]), "r"(od[9]), "r"(od[10]),
+          "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]), "r"(c0));
+}
+// a + b as a plain integer (both canonical: the sum is below 2p < 2^256)
+__device__ __forceinline__ Fr add_plain(const Fr& a, const Fr& b) {
+    Fr r;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;\n\t"
+        : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+        : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]), "r"(b.l[0]), "r"(b.l[1]),
+          "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+    return r;
+}
+
+// 16 limbs (64 bytes) of pair `row` into a [pairs][128 B] SWIZZLE_128B operand at 16-byte chunks c0..c0+3 of the row
+__device__ __forceinline__ void sts_sw128(uint8_t* base, uint32_t row, uint32_t c0, const uint32_t* v) {
+#pragma unroll
+    for (uint32_t c = 0; c < 4; c++)
+        *reinterpret_cast<uint4*>(base + row * 128u + (((c0 + c) ^ (row & 7u)) << 4)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+// ... into a [pairs][64 B] SWIZZLE_64B operand
+__device__ __forceinline__ void sts_sw64(uint8_t* base, uint32_t row, const uint32_t* v) {
+#pragma unroll
+    for (uint32_t c = 0; c < 4; c++)
+        *reinterpret_cast<uint4*>(base + row * 64u + ((c ^ ((row >> 1) & 3u)) << 4)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+
+// The three products of one pair into the group's X operand: XA row = [q0 | q1] (SWIZZLE_128B), XQ row = qs (SWIZZLE_64B)
+__device__ __forceinline__ void products_to_smem(const Fr& a0, const Fr& b0, const Fr& a1, const Fr& b1, uint8_t* XA, uint8_t* XQ, uint32_t row) {
+    uint32_t o[16];
+    mul_plain(a0, a1, o);
+    sts_sw128(XA, row, 0, o);
+    mul_plain(b0, b1, o);
+    sts_sw128(XA, row, 4, o);
+    mul_plain(add_plain(a0, b0), add_plain(a1, b1), o);
+    sts_sw64(XQ, row, o);
+}
+
+// ---- contraction of one 128-pair tile: D1 (128 x 64) += XA^T Y, D2 (64 x 64) += XQ^T Y; issued by ONE thread ----------------------
+__device__ __forceinline__ void issue_contraction(uint32_t xa_smem, uint32_t xq_smem, uint32_t y_smem, uint32_t tmem_d, uint32_t accumulate) {
+    constexpr uint32_t I128 = idesc_u8_mn(128, 64), I64 = idesc_u8_mn(64, 64);
+#pragma unroll
+    for (uint32_t ks = 0; ks < 4; ks++) {
+        const uint64_t b = mn_desc(y_smem + ks * 2048u, 512, 4);
+        umma(tmem_d, mn_desc(xa_smem + ks * 4096u, 1024, 2), b, I128, accumulate | ks);
+        umma(tmem_d + 64, mn_desc(xq_smem + ks * 2048u, 512, 4), b, I64, accumulate | ks);
+    }
+}
+
+// ---- epilogue: D -> anti-diagonal sums -> global totals -> (last CTA) the six integers --------------------------------------------
+// Degree-3 layout: D1 lanes 0..127 = byte u of q0 (lanes 0..63) / q1 (64..127), D2 rows 0..63 = byte u of qs in lanes
+// (u % 16) + 32 (u / 16); columns 0..31 = byte v of y0 = a2, 32..63 = byte v of y1 = b2.  Block pair bp = 2 i + j, diagonal k = u + v.
+constexpr uint32_t NB3 = 6, DIAG3 = 95, OUT_LIMBS3 = 26;
+
+// s_E: [2][NB3 * 96] (low / high 16-bit halves of the accumulators, summed as u32).  Called by the whole CTA; warps 0..3 read TMEM.
+__device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool has_work, uint32_t* s_E, bool* s_last) {
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (uint32_t i = tid; i < 2 * NB3 * 96; i += blockDim.x) s_E[i] = 0;
+    __syncthreads();
+    tcf::tc_fence_after();
+    if (warp < 4 && has_work) {  // (a CTA without work never wrote its accumulators)
+        const uint32_t lane_addr = tmem_d + ((warp * 32u) << 16);
+        uint32_t S[32];
+#pragma unroll 1
+        for (uint32_t part = 0; part < 4; part++) {  // D1 columns 0..31, 32..63, D2 columns 0..31, 32..63
+            const bool second = part >= 2;
+            tcf::tmem_ld32(lane_addr + part * 32u, S);  // (whole warp: .sync.aligned)
+            tcf::tmem_ld_wait();
+            if (second && lane >= 16) continue;  // D2 (M = 64) lives in lanes 0..15 of every 32-lane quadrant
+            const uint32_t i = second ? 2u : (tid >> 6), u = second ? (warp * 16u + lane) : (tid & 63u), j = part & 1u;
+            uint32_t* lo = s_E + (2 * i + j) * 96 + u;
+            uint32_t* hi = lo + NB3 * 96;
+#pragma unroll
+            for (int v = 0; v < 32; v++) {
+                atomicAdd(lo + v, S[v] & 0xffffu);
+                atomicAdd(hi + v, S[v] >> 16);
+            }
+        }
+    }
+    tcf::tc_fence_before();
+    __syncthreads();
+    for (uint32_t i = tid; i < NB3 * 96; i += blockDim.x) {
+        const uint32_t bp = i / 96, k = i % 96;
+        if (k >= DIAG3) continue;
+        const unsigned long long v = (unsigned long long)s_E[i] + ((unsigned long long)s_E[NB3 * 96 + i] << 16);
+        if (v) atomicAdd(P.totals + bp * TOT_STRIDE + k, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int ticket = atomicAdd(P.rp.counter, 1u);
+        *s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!*s_last) return;
+    __threadfence();
+    if (tid == 0) *P.rp.counter = 0;
+    if (!P.publish) return;
+    if (tid < NB3) {  // Z = sum_k 2^(8k) totals[k]: byte-serial carry into OUT_LIMBS3 limbs
+        unsigned long long acc = 0;
+        uint32_t limb = 0;
+        for (uint32_t k = 0; k < OUT_LIMBS3 * 4; k++) {
+            if (k < DIAG3) {
+                acc += __ldcg(P.totals + tid * TOT_STRIDE + k);
+                P.totals[tid * TOT_STRIDE + k] = 0;
+            }
+            limb |= (uint32_t)(acc & 0xffu) << (8 * (k & 3u));
+            acc >>= 8;
+            if ((k & 3u) == 3u) {
+                P.rp.host_out[tid * OUT_LIMBS3 + (k >> 2)] = limb;
+                limb = 0;
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0 && P.rp.host_flag) *P.rp.host_flag = P.rp.seq;
+}
+
+// ================================================================================================ round 1 (no fold), degree 3
+// Tables 0 and 1 of the product are read by the threads (two LDG.256 per table), table 2 goes HBM -> shared memory by TMA with
+// 64-byte rows and is the Y operand as it lands.
+template <int G>
+struct R1Smem {
+    static constexpr uint32_t XA = 0, XQ = 16384, Y0 = 24576, Y1 = 32768, GROUP = 40960;
+    static constexpr size_t BYTES = (size_t)G * GROUP;
+};
+
+template <int G>
+__global__ void __launch_bounds__(G * 128 + 64, 1) gemm_round1_kernel(const Params P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t y_full[G][2], y_empty[G][2], x_full[G], x_empty[G];
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_E[2 * NB3 * 96];
+    __shared__ bool s_last;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const sck::RoundParams& p = P.rp;
+    if (tid == 0) {
+        if (tcf::smem_u32(smem) & 1023u) __trap();
+        for (int g = 0; g < G; g++) {
+            tcf::mbar_init(&y_full[g][0], 1);
+            tcf::mbar_init(&y_full[g][1], 1);
+            tcf::mbar_init(&y_empty[g][0], 1);
+            tcf::mbar_init(&y_empty[g][1], 1);
+            tcf::mbar_init(&x_full[g], 4);
+            tcf::mbar_init(&x_empty[g], 1);
+        }
+        tcf::fence_mbar_init();
+    }
+    if (warp == 0) tcf::tmem_alloc(&s_tmem, 128);
+    tcf::tc_fence_before();
+    __syncthreads();
+    tcf::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t stride = gridDim.x * G;
+    // items of group g: w = blockIdx.x * G + g + n * stride < P.items
+    auto items_of = [&](uint32_t g) {
+        const uint32_t first = blockIdx.x * G + g;
+        return first < P.items ? (P.items - first + stride - 1) / stride : 0u;
+    };
+    if (warp < G * 4) {
+        // ---------------------------------------------------------------------------------------------------- compute group
+        const uint32_t g = warp >> 2, t = tid & 127u;
+        uint8_t* const base = smem + (size_t)g * R1Smem<G>::GROUP;
+        const uint32_t n_items = items_of(g);
+        for (uint32_t n = 0; n < n_items; n++) {
+            const uint32_t w = blockIdx.x * G + g + n * stride;
+            const uint32_t k = w % p.n_products, tile = p.tile_base + w / p.n_products;
+            const uint32_t j0 = p.prod_offsets[k];
+            const unsigned long long b = (unsigned long long)tile * TILE + t;
+            const uint32_t* s0 = p.tab_in[p.prod_indices[j0]] + b * 16;
+            const uint32_t* s1 = p.tab_in[p.prod_indices[j0 + 1]] + b * 16;
+            const Fr a0 = fr::load_stream(s0), b0 = fr::load_stream(s0 + 8), a1 = fr::load_stream(s1), b1 = fr::load_stream(s1 + 8);
+            if (n > 0) tcf::mbar_wait(&x_empty[g], (n - 1) & 1u);  // the contraction of item n-1 has read the X operand
+            products_to_smem(a0, b0, a1, b1, base + R1Smem<G>::XA, base + R1Smem<G>::XQ, t);
+            tcf::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tcf::mbar_arrive(&x_full[g]);
+        }
+    } else if (warp == G * 4) {
+        // ---------------------------------------------------------------------------------------------------- P0: TMA of the Y tiles
+        if (lane == 0) {
+            uint32_t n_items[G], max_items = 0;
+            for (int g = 0; g < G; g++) {
+                n_items[g] = items_of(g);
+                max_items = n_items[g] > max_items ? n_items[g] : max_items;
+            }
+            for (uint32_t n = 0; n < max_items; n++)
+                for (int g = 0; g < G; g++) {
+                    if (n >= n_items[g]) continue;
+                    const uint32_t s = n & 1u;
+                    if (n >= 2) tcf::mbar_wait(&y_empty[g][s], ((n >> 1) - 1u) & 1u);
+                    const uint32_t w = blockIdx.x * G + g + n * stride;
+                    const uint32_t k = w % p.n_products, tile = p.tile_base + w / p.n_products;
+                    const uint32_t idx = p.prod_indices[p.prod_offsets[k] + 2];
+                    tcf::mbar_expect_tx(&y_full[g][s], 8192);
+                    tcf::tma_load_tile(smem + (size_t)g * R1Smem<G>::GROUP + (s ? R1Smem<G>::Y1 : R1Smem<G>::Y0), (const uint8_t*)P.ymaps + (size_t)idx * 128,
+                                       &y_full[g][s], tile * TILE);
+                }
+        }
+    } else {
+        // ---------------------------------------------------------------------------------------------------- P1: contraction MMAs
+        if (lane == 0) {
+            uint32_t n_items[G], max_items = 0;
+            for (int g = 0; g < G; g++) {
+                n_items[g] = items_of(g);
+                max_items = n_items[g] > max_items ? n_items[g] : max_items;
+            }
+            uint32_t acc = 0;
+            for (uint32_t n = 0; n < max_items; n++)
+                for (int g = 0; g < G; g++) {
+                    if (n >= n_items[g]) continue;
+                    const uint32_t s = n & 1u, gb = tcf::smem_u32(smem + (size_t)g * R1Smem<G>::GROUP);
+                    tcf::mbar_wait(&y_full[g][s], (n >> 1) & 1u);
+                    tcf::mbar_wait(&x_full[g], n & 1u);
+                    tcf::tc_fence_after();
+                    issue_contraction(gb + R1Smem<G>::XA, gb + R1Smem<G>::XQ, gb + (s ? R1Smem<G>::Y1 : R1Smem<G>::Y0), tmem, acc);
+                    acc = 1;
+                    tcf::umma_commit(&x_empty[g]);
+                    tcf::umma_commit(&y_empty[g][s]);
+                }
+            // every MMA has completed once the last commit of every group has arrived
+            for (int g = 0; g < G; g++)
+                if (n_items[g]) tcf::mbar_wait(&x_empty[g], (n_items[g] - 1) & 1u);
+        }
+    }
+    __syncwarp();
+    tcf::tc_fence_before();
+    __syncthreads();
+    epilogue3(P, tmem, items_of(0) > 0, s_E, &s_last);
+    __syncthreads();
+    if (warp == 0) tcf::tmem_dealloc(tmem, 128);
+}
+
+// ================================================================================================ fold rounds, degree 3
+// Every table tile (128 rows x 128 bytes = old[4b..4b+3]) goes HBM -> shared memory by TMA into a ring shared by the groups;
+// P0 issues the fix_variables MMAs (tc_fold.cuh) into the owning group's accumulator (two per group, alternating); the group's
+// thread t reads out new[2b], new[2b+1] of pair b = tile * 128 + t, stores them (the folded table) and, once it holds the pairs
+// of the product's first two tables, writes the three plain products; the folded pair of the third table is the Y operand.
+template <int G>
+struct FoldSmem {
+    static constexpr uint32_t RING_SLOTS = 6;
+    static constexpr uint32_t GROUPS = RING_SLOTS * tcf::TILE_BYTES;
+    static constexpr uint32_t XA = 0, XQ = 16384, Y = 24576, GROUP = 32768;
+    static constexpr uint32_t BMAT = GROUPS + G * GROUP;
+    static constexpr size_t BYTES = (size_t)BMAT + tcf::BMAT_BYTES;
+};
+
+// the order in which P0 walks the (item n, multiplicand j, group g) units of a CTA: j inside n, g innermost, so that
+// consecutive units belong to different groups and a group's two accumulators are rarely both busy
+template <int G>
+struct UnitCursor {
+    uint32_t n = 0, j = 0, g = 0;
+    const uint32_t* n_items;
+    __device__ __forceinline__ explicit UnitCursor(const uint32_t* ni) : n_items(ni) { settle(); }
+    __device__ __forceinline__ void settle() {
+        while (n_items[g] <= n) {  // the caller never walks past the last unit
+            if (++g == G) { g = 0; if (++j == 3) { j = 0; n++; } }
+        }
+    }
+    __device__ __forceinline__ void next() {
+        if (++g == G) { g = 0; if (++j == 3) { j = 0; n++; } }
+    }
+};
+
+template <int G>
+__global__ void __launch_bounds__(G * 128 + 64, 1) gemm_fold_kernel(const Params P) {
+    using L = FoldSmem<G>;
+    constexpr uint32_t R = L::RING_SLOTS;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t slot_full[R], slot_empty[R], acc_full[G][2], acc_empty[G][2], x_full[G], x_empty[G];
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_E[2 * NB3 * 96];
+    __shared__ bool s_last;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const sck::RoundParams& p = P.rp;
+    uint8_t* const bmat = smem + L::BMAT;
+    if (tid == 0) {
+        if (tcf::smem_u32(smem) & 1023u) __trap();
+        for (uint32_t s = 0; s < R; s++) {
+            tcf::mbar_init(&slot_full[s], 1);
+            tcf::mbar_init(&slot_empty[s], 1);
+        }
+        for (int g = 0; g < G; g++) {
+            tcf::mbar_init(&acc_full[g][0], 1);
+            tcf::mbar_init(&acc_full[g][1], 1);
+            tcf::mbar_init(&acc_empty[g][0], 4);
+            tcf::mbar_init(&acc_empty[g][1], 4);
+            tcf::mbar_init(&x_full[g], 4);
+            tcf::mbar_init(&x_empty[g], 1);
+        }
+        tcf::fence_mbar_init();
+    }
+    if (warp == 0) tcf::tmem_alloc(&s_tmem, 512);
+    {
+        Fr r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.l[i] = p.r[i];
+        tcf::build_bmat(r, bmat);
+    }
+    tcf::fence_proxy_async_smem();
+    tcf::tc_fence_before();
+    __syncthreads();
+    tcf::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t stride = gridDim.x * G;
+    auto items_of = [&](uint32_t g) {
+        const uint32_t first = blockIdx.x * G + g;
+        return first < P.items ? (P.items - first + stride - 1) / stride : 0u;
+    };
+    if (warp < G * 4) {
+        // ---------------------------------------------------------------------------------------------------- compute group
+        const uint32_t g = warp >> 2, t = tid & 127u;
+        uint8_t* const base = smem + L::GROUPS + (size_t)g * L::GROUP;
+        const uint32_t lane_taddr = tmem + 128u + g * 128u + (((warp & 3u) * 32u) << 16);
+        const uint32_t n_items = items_of(g);
+        for (uint32_t n = 0; n < n_items; n++) {
+            const uint32_t w = blockIdx.x * G + g + n * stride;
+            const uint32_t k = w % p.n_products, tile = p.tile_base + w / p.n_products;
+            const uint32_t j0 = p.prod_offsets[k];
+            const unsigned long long b = (unsigned long long)tile * TILE + t;
+            Fr e0, o0;
+#pragma unroll
+            for (uint32_t j = 0; j < 3; j++) {
+                const uint32_t q = 3 * n + j, a = q & 1u;
+                tcf::mbar_wait(&acc_full[g][a], (q >> 1) & 1u);
+                tcf::tc_fence_after();
+                uint32_t S[32];
+                tcf::tmem_ld32(lane_taddr + a * 64u, S);
+                tcf::tmem_ld_wait();
+                const Fr v0 = tcf::columns_to_fr(S);
+                tcf::tmem_ld32(lane_taddr + a * 64u + 32u, S);
+                tcf::tmem_ld_wait();
+                tcf::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tcf::mbar_arrive(&acc_empty[g][a]);
+                const Fr v1 = tcf::columns_to_fr(S);
+                const uint32_t jj = j0 + j;
+                if (p.write_fold && p.prod_first[jj]) {
+                    uint32_t* dst = p.tab_out[p.prod_indices[jj]] + b * 16;
+                    fr::store(dst, v0);
+                    fr::store(dst + 8, v1);
+                }
+                if (j == 0) {
+                    e0 = v0;
+                    o0 = v1;
+                } else if (j == 1) {
+                    if (n > 0) tcf::mbar_wait(&x_empty[g], (n - 1) & 1u);  // the contraction of item n-1 has read X and Y
+                    products_to_smem(e0, o0, v0, v1, base + L::XA, base + L::XQ, t);
+                } else {
+                    uint32_t y[16];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        y[i] = v0.l[i];
+                        y[8 + i] = v1.l[i];
+                    }
+                    sts_sw64(base + L::Y, t, y);
+                }
+            }
+            tcf::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tcf::mbar_arrive(&x_full[g]);
+        }
+    } else if (warp == G * 4) {
+        // ---------------------------------------------------------------------------------------------------- P0: TMA + fold MMAs
+        if (lane == 0) {
+            uint32_t n_items[G], U = 0;
+            for (int g = 0; g < G; g++) {
+                n_items[g] = items_of(g);
+                U += 3 * n_items[g];
+            }
+            if (U) {
+                UnitCursor<G> ct(n_items), cm(n_items);
+                const uint32_t ring = tcf::smem_u32(smem), bmat_smem = tcf::smem_u32(bmat);
+                uint32_t u_tma = 0;
+                auto issue_tma = [&](uint32_t slot) {
+                    const uint32_t w = blockIdx.x * G + ct.g + ct.n * stride;
+                    const uint32_t k = w % p.n_products, tile = p.tile_base + w / p.n_products;
+                    const uint32_t idx = p.prod_indices[p.prod_offsets[k] + ct.j];
+                    tcf::mbar_expect_tx(&slot_full[slot], tcf::TILE_BYTES);
+                    tcf::tma_load_tile(smem + (size_t)slot * tcf::TILE_BYTES, (const uint8_t*)p.tmaps + (size_t)idx * 128, &slot_full[slot], tile * TILE);
+                    u_tma++;
+                    if (u_tma < U) {
+                        ct.next();
+                        ct.settle();
+                    }
+                };
+                while (u_tma < R && u_tma < U) issue_tma(u_tma);
+                for (uint32_t u = 0; u < U; u++) {
+                    const uint32_t slot = u % R;
+                    tcf::mbar_wait(&slot_full[slot], (u / R) & 1u);
+                    const uint32_t q = 3 * cm.n + cm.j, a = q & 1u;
+                    if (q >= 2) tcf::mbar_wait(&acc_empty[cm.g][a], ((q >> 1) - 1u) & 1u);
+                    tcf::tc_fence_after();
+                    tcf::issue_fold_mma(ring + slot * tcf::TILE_BYTES, bmat_smem, tmem + 128u + cm.g * 128u + a * 64u);
+                    tcf::umma_commit(&acc_full[cm.g][a]);
+                    tcf::umma_commit(&slot_empty[slot]);
+                    if (u >= 1 && u_tma < U) {  // refill the slot of the previous unit: its MMAs have (all but) completed
+                        const uint32_t ps = (u - 1) % R;
+                        tcf::mbar_wait(&slot_empty[ps], ((u - 1) / R) & 1u);
+                        issue_tma(ps);
+                    }
+                    if (u + 1 < U) {
+                        cm.next();
+                        cm.settle();
+                    }
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------------------------------------- P1: contraction MMAs
+        if (lane == 0) {
+            uint32_t n_items[G], max_items = 0;
+            for (int g = 0; g < G; g++) {
+                n_items[g] = items_of(g);
+                max_items = n_items[g] > max_items ? n_items[g] : max_items;
+            }
+            uint32_t acc = 0;
+            for (uint32_t n = 0; n < max_items; n++)
+                for (int g = 0; g < G; g++) {
+                    if (n >= n_items[g]) continue;
+                    const uint32_t gb = tcf::smem_u32(smem + L::GROUPS + (size_t)g * L::GROUP);
+                    tcf::mbar_wait(&x_full[g], n & 1u);
+                    tcf::tc_fence_after();
+                    issue_contraction(gb + L::XA, gb + L::XQ, gb + L::Y, tmem, acc);
+                    acc = 1;
+                    tcf::umma_commit(&x_empty[g]);
+                }
+            for (int g = 0; g < G; g++)
+                if (n_items[g]) tcf::mbar_wait(&x_empty[g], (n_items[g] - 1) & 1u);
+        }
+    }
+    __syncwarp();
+    tcf::tc_fence_before();
+    __syncthreads();
+    epilogue3(P, tmem, items_of(0) > 0, s_E, &s_last);
+    __syncthreads();
+    if (warp == 0) tcf::tmem_dealloc(tmem, 512);
+}
+
+// ---- launchers (gemm.cu) ------------------------------------------------------------------------------------------------------------
+cudaError_t init_constants();
+int groups_round1();
+int groups_fold();
+unsigned long long max_items_round1(int sms);  // work items one launch may carry (s32 accumulator head-room)
+unsigned long long max_items_fold(int sms);
+cudaError_t launch_round1(const Params& P, int sms, cudaStream_t stream);
+cudaError_t launch_fold(const Params& P, int sms, cudaStream_t stream);
+
+}  // namespace gsum

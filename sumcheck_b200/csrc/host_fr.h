@@ -211,4 +211,61 @@ inline F interpolate(const F* evals, uint32_t d, const F& r) {
     return acc;
 }
 
+// ---- tensor-core contraction rounds (gemm_sum.cuh) ------------------------------------------------------------------------------
+// V mod p (a RAW residue, not Montgomery) of an n-limb (32-bit) integer: Horner over 256-bit chunks, acc * 2^256 = mul(acc, R^2).
+inline F reduce_limbs(const uint32_t* v, uint32_t n) {
+    F acc = {{0, 0, 0, 0}};
+    for (int c = (int)((n + 7) / 8) - 1; c >= 0; c--) {
+        F chunk = {{0, 0, 0, 0}};
+        for (uint32_t i = 0; i < 8 && (uint32_t)c * 8 + i < n; i++) chunk.l[i >> 1] |= (uint64_t)v[(uint32_t)c * 8 + i] << (32 * (i & 1));
+        for (int k = 0; k < 2; k++)  // 2^256 < 3p
+            if (geq_p(chunk.l)) sub_p(chunk.l);
+        acc = add(mul(acc, R2), chunk);
+    }
+    return acc;
+}
+
+// One product of m multiplicands split into an X side of kx and a Y side of ky = m - kx multiplicands (kx, ky in {1, 2}).  A side
+// of ONE table contributes the values (a, b) = (table[2b], table[2b+1]): its line is (1-t) a + t b.  A side of TWO tables
+// contributes (q0, q1, qs) = (a a', b b', (a+b)(a'+b')): the product of its two lines is (1-t)^2 q0 + t(1-t)(qs - q0 - q1) + t^2 q1.
+// z[i * ny + j] = limbs of sum_b X_i * Y_j (n_limbs each, plain integers of Montgomery-form operands, i.e. value * R^m).
+// out[t] = P(t) for t = 0..d in Montgomery form (unscaled by any deferred coefficient).
+inline void side_weights(uint32_t k, long long t, F* w) {
+    if (k == 1) {
+        w[0] = from_i64(1 - t);
+        w[1] = from_i64(t);
+    } else {
+        w[0] = from_i64((1 - t) * (1 - 2 * t));
+        w[1] = from_i64(t * (2 * t - 1));
+        w[2] = from_i64(t * (1 - t));
+    }
+}
+inline void gemm_finish(const uint32_t* z, uint32_t n_limbs, uint32_t kx, uint32_t ky, uint32_t d, F* out) {
+    const uint32_t nx = kx == 1 ? 2 : 3, ny = ky == 1 ? 2 : 3, m = kx + ky;
+    const F one_int = {{1, 0, 0, 0}};
+    F Z[9];
+    for (uint32_t i = 0; i < nx * ny; i++) {
+        F v = reduce_limbs(z + (size_t)i * n_limbs, n_limbs);      // value * R^m mod p
+        for (uint32_t k = 1; k < m; k++) v = mul(v, one_int);      // -> value * R (Montgomery form)
+        Z[i] = v;
+    }
+    for (uint32_t t = 0; t <= d; t++) {
+        F wx[3], wy[3], acc = {{0, 0, 0, 0}};
+        side_weights(kx, (long long)t, wx);
+        side_weights(ky, (long long)t, wy);
+        for (uint32_t i = 0; i < nx; i++)
+            for (uint32_t j = 0; j < ny; j++) acc = add(acc, mul(mul(wx[i], wy[j]), Z[i * ny + j]));
+        out[t] = acc;
+    }
+}
+// a += b for n-limb integers (the pieces of a round summed by several launches)
+inline void add_limbs(uint32_t* a, const uint32_t* b, uint32_t n) {
+    uint64_t c = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        c += (uint64_t)a[i] + b[i];
+        a[i] = (uint32_t)c;
+        c >>= 32;
+    }
+}
+
 }  // namespace hfr

@@ -26,6 +26,7 @@
 #include "host_fr.h"
 #include "host_copy.h"
 #include "tma_round1.cuh"
+#include "gemm_sum.cuh"
 
 static_assert(sizeof(sc_blake2b512_rng) == sizeof(b2::State), "sc_blake2b512_rng must be layout-identical to b2::State");
 
@@ -96,6 +97,7 @@ int ensure_device(int device) {
         if (prop.major < 10) return fail(SC_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
         CUDA_TRY(fr::fr_init_constants());
         CUDA_TRY(sck::tail_init_constants());
+        CUDA_TRY(gsum::init_constants());
         g_dev[device].sms = prop.multiProcessorCount;
         cudaDeviceGetAttribute(&g_dev[device].khz, cudaDevAttrClockRate, device);
         g_dev[device].ready = true;
@@ -261,6 +263,7 @@ struct sc_prover {
     // Pipelined upload (sc_prover_load_tables): the tables arrive in EAGER_CHUNKS pieces on a copy stream while round 1 —
     // which needs no challenge — is summed piece by piece behind them; the first prove_round then only adds the pieces up.
     bool eager_valid = false;
+    bool eager_gemm = false;  // the chunks were summed by the contraction kernel: six integers per chunk in h_gemm slots 1..
     uint32_t eager_epoch = 0;
     uint32_t* h_eager = nullptr;   // pinned+mapped: [EAGER_CHUNKS][(MAX_NPTS * 8) sums + 8 (flag word first)]
     uint32_t* d_eager = nullptr;
@@ -271,7 +274,15 @@ struct sc_prover {
     bool direct_results = true;  // rounds deliver their message through mapped host memory + flag
     bool direct_active = false;  // ... and the round just issued did so
     bool exchange = false;       // sharded round: fuse the partial-sum exchange into the round kernel
-    uint64_t launches = 0, tc_rounds = 0, res_rounds = 0;
+    uint64_t launches = 0, tc_rounds = 0, res_rounds = 0, gemm_rounds = 0;
+    // Tensor-core contraction rounds (gemm_sum.cuh): products of three tables; the sums arrive as big integers in h_gemm
+    bool gemm_shape = false;     // the list of products has the shape those kernels serve
+    bool gemm_r1_ok = false;     // ... and the 64-byte-row descriptors of the pristine tables exist (round 1)
+    bool gemm_active = false;    // the round just issued delivers through h_gemm
+    uint8_t* d_ymaps = nullptr;  // [T] CUtensorMap: tab0 as rows of one pair (64 bytes), SWIZZLE_64B, 128-row boxes
+    std::vector<CUtensorMap> h_ymaps;
+    unsigned long long* d_gemm_totals = nullptr;
+    uint32_t *h_gemm = nullptr, *d_gemm = nullptr;  // mapped: [1 + EAGER_CHUNKS] slots of gsum::OUT_SLOT_WORDS
     // where the d+1 results of the last round live on the device (local buffers, the summed copies, or the sub-prover's)
     uint32_t *out_evals = nullptr, *out_canon = nullptr;
     // ---- multi-GPU (capi_multi.inc): nv is GLOBAL, nv_local = nv - log2(ranks) is what this rank's shard spans
@@ -415,6 +426,49 @@ int multi_ml_prove(sc_prover* P, sc_blake2b512_rng* rng, uint64_t* evals_out, ui
 int multi_table(const sc_prover* P, uint32_t j, uint64_t* out, uint64_t cap_elems, uint64_t* len_out);
 inline const sc_prover* lead(const sc_prover* p) { return (p && !p->group.empty()) ? p->group[0] : p; }
 
+// ---- tensor-core contraction rounds (gemm_sum.cuh) --------------------------------------------------------------------------------
+constexpr uint32_t GEMM_LIMBS3 = gsum::OUT_LIMBS3, GEMM_NB3 = gsum::NB3;
+
+// May this round (n_pairs output pairs; fold = rounds >= 2) run on the contraction kernels?
+bool gemm_round_ok(const sc_prover* p, unsigned long long n_pairs, bool fold) {
+    if (!p->gemm_shape || p->comm || p->is_shard || !p->host_post || !p->direct_results) return false;
+    if (p->n_products > 1)
+        for (uint32_t k = 0; k < p->n_products; k++)
+            if (!p->h_scaled[k]) return false;  // a coefficient that is not inside a table would have to be applied per product
+    if (n_pairs < p->tc_min_pairs || n_pairs % gsum::TILE) return false;
+    return fold ? p->tc_buf_ok[p->cur] : (p->gemm_r1_ok && p->cur == 0);
+}
+
+// Launch the round over the tiles [tile0, tile0 + n_tiles) (several launches when one could overflow the s32 accumulators); the
+// last launch publishes the six integers into mapped slot `slot` of h_gemm and then `seq` into the slot's last word.
+int launch_gemm_round(sc_prover* p, const sck::RoundParams& rp, bool fold, unsigned long long tile0, unsigned long long n_tiles, uint32_t slot, uint32_t seq) {
+    gsum::Params G;
+    memset(&G, 0, sizeof(G));
+    G.rp = rp;
+    G.ymaps = p->d_ymaps;
+    G.totals = p->d_gemm_totals;
+    G.rp.host_out = p->d_gemm + (size_t)slot * gsum::OUT_SLOT_WORDS;
+    G.rp.host_flag = G.rp.host_out + gsum::OUT_SLOT_WORDS - 1;
+    G.rp.seq = seq;
+    const int sms = g_dev[p->device].sms;
+    unsigned long long cap = (fold ? gsum::max_items_fold(sms) : gsum::max_items_round1(sms)) / p->n_products;  // tiles per launch
+    if (const char* env = getenv("SC_GEMM_MAX_TILES")) {  // tests: force the several-launches-per-round path at small sizes
+        const unsigned long long v = strtoull(env, nullptr, 10);
+        if (v >= 1 && v < cap) cap = v;
+    }
+    if (cap < 1) cap = 1;
+    for (unsigned long long t = 0; t < n_tiles; t += cap) {
+        const unsigned long long take = n_tiles - t < cap ? n_tiles - t : cap;
+        G.rp.tile_base = (uint32_t)(tile0 + t);
+        G.items = (uint32_t)(take * p->n_products);
+        G.publish = (t + take == n_tiles) ? 1u : 0u;
+        p->launches++;
+        cudaError_t e = fold ? gsum::launch_fold(G, sms, p->stream) : gsum::launch_round1(G, sms, p->stream);
+        if (e != cudaSuccess) return fail(SC_ERR_CUDA, "contraction kernel launch: %s", cudaGetErrorString(e));
+    }
+    return SC_OK;
+}
+
 // One protocol round on the device: (fold on r) + sums for all d+1 points.  Results land in d_evals / d_canon.
 int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
     const uint32_t i = p->round;  // already incremented: 1-based round being computed
@@ -458,6 +512,22 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
     }
     p->raw_active = false;
     p->alt_active = false;
+    p->gemm_active = false;
+    if (direct && gemm_round_ok(p, rp.n_pairs, fold)) {
+        // products of three tables: the per-pair work shrinks to three plain products, the sum runs on the tensor cores and the
+        // host turns the six integers it receives into P(0..d) (host_finish_round)
+        rp.write_fold = 1;
+        rp.tmaps = fold ? p->d_maps + (size_t)p->cur * p->T * sizeof(CUtensorMap) : nullptr;
+        int rc = launch_gemm_round(p, rp, fold, 0, rp.n_pairs / gsum::TILE, 0, rp.seq);
+        if (rc) return rc;
+        p->gemm_active = true;
+        p->raw_active = true;
+        p->used_skip1 = false;
+        p->gemm_rounds++;
+        if (fold) p->tc_rounds++;
+        p->cur = next;
+        return SC_OK;
+    }
     if (fold && p->d <= (uint32_t)sck::MAX_NPTS && p->d_lagrange) {
         // rounds >= 2: P(0) + P(1) = P_prev(r) (the verifier's check, verifier.rs:109), so only t = 0, 2, .., d are summed
         rp.skip1 = 1;
@@ -606,6 +676,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     const size_t oMaps = take((size_t)4 * T * sizeof(CUtensorMap));
     const size_t oScaled = take(n_products);
     const size_t oResB = take(RES_BCAST_BYTES), oResC = take(64 * sizeof(unsigned int));
+    const size_t oYmaps = take((size_t)T * sizeof(CUtensorMap)), oGemmTot = take((size_t)9 * gsum::TOT_STRIDE * sizeof(unsigned long long));
     TRY_P(device_alloc((void**)&p->slabA, off, &p->slabA_bytes, device));
     uint8_t* base = (uint8_t*)p->slabA;
     for (uint32_t j = 0; j < T; j++) {
@@ -618,6 +689,9 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     p->d_evals = (uint32_t*)(base + oEv); p->d_canon = (uint32_t*)(base + oCa);
     p->d_res_bcast = (uint32_t*)(base + oResB); p->d_res_counters = (unsigned int*)(base + oResC);
     TRY_P(cudaMemsetAsync(p->d_res_bcast, 0, RES_BCAST_BYTES, p->stream));  // a recycled slab may hold another handle's sequence numbers
+    p->d_ymaps = base + oYmaps;
+    p->d_gemm_totals = (unsigned long long*)(base + oGemmTot);
+    TRY_P(cudaMemsetAsync(p->d_gemm_totals, 0, (size_t)9 * gsum::TOT_STRIDE * sizeof(unsigned long long), p->stream));
     p->d_tail_evals = (uint32_t*)(base + oTe); p->d_tail_chal = (uint32_t*)(base + oTc); p->d_st = (b2::State*)(base + oSt);
     {
         // TMA descriptors (fold rounds with >= tc_min_pairs output pairs run on the TMA + tensor-core kernel)
@@ -684,6 +758,20 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
             TRY_P(cudaMemcpyAsync(p->d_scaled, p->h_scaled.data(), n_products, cudaMemcpyHostToDevice, p->stream));
         }
     }
+    {
+        // Tensor-core contraction rounds (gemm_sum.cuh): every product has exactly three multiplicands; with several products
+        // every coefficient must already live in a table (checked per round: gemm_round_ok)
+        bool shape = d == 3 && !getenv("SC_NO_GEMM") && !getenv("SC_NO_TC");
+        for (uint32_t k = 0; k < n_products && shape; k++) shape = offsets[k + 1] - offsets[k] == 3;
+        p->gemm_shape = shape;
+        if (shape && N / 2 >= gsum::TILE) {
+            p->h_ymaps.resize(T);
+            bool ok = true;
+            for (uint32_t j = 0; j < T && ok; j++) ok = tmaph::make_pair_map(&p->h_ymaps[j], p->tab0[j], N / 2, gsum::TILE);
+            p->gemm_r1_ok = ok;
+            if (ok) TRY_P(cudaMemcpyAsync(p->d_ymaps, p->h_ymaps.data(), (size_t)T * sizeof(CUtensorMap), cudaMemcpyHostToDevice, p->stream));
+        }
+    }
     if (d + 1 <= 32) {  // Lagrange weights + the nodes 0..d for the P(1)-from-claim shortcut: host table (cached per degree)
         p->d_lagrange = (uint32_t*)(base + oLag);
         p->h_lagrange = lagrange_block(d);
@@ -691,7 +779,8 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     }
     const size_t hRes = up((size_t)(d + 1) * 64 + 64), hTail = up((size_t)nv * (d + 2) * 32), hSt = up(2 * sizeof(b2::State));
     const size_t hEager = up((size_t)EAGER_CHUNKS * EAGER_SLOT_WORDS * 4);
-    TRY_P(host_mapped_alloc((void**)&p->h_result, hRes + hTail + hSt + hEager + RES_HOST_BYTES, &p->h_result_bytes, device));
+    const size_t hGemm = up((size_t)(1 + EAGER_CHUNKS) * gsum::OUT_SLOT_WORDS * 4);
+    TRY_P(host_mapped_alloc((void**)&p->h_result, hRes + hTail + hSt + hEager + up(RES_HOST_BYTES) + hGemm, &p->h_result_bytes, device));
     memset(p->h_result, 0, hRes);
     TRY_P(cudaHostGetDevicePointer((void**)&p->d_result, p->h_result, 0));
     p->h_evals = p->h_result;
@@ -704,6 +793,9 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     p->h_res = (uint32_t*)((uint8_t*)p->h_result + hRes + hTail + hSt + hEager);
     p->d_res = (uint32_t*)((uint8_t*)p->d_result + hRes + hTail + hSt + hEager);
     memset(p->h_res, 0, RES_HOST_BYTES);  // recycled pinned blocks hold another handle's sequence numbers
+    p->h_gemm = (uint32_t*)((uint8_t*)p->h_res + up(RES_HOST_BYTES));
+    p->d_gemm = (uint32_t*)((uint8_t*)p->d_res + up(RES_HOST_BYTES));
+    memset(p->h_gemm, 0, hGemm);
     {
         const char* env = getenv("SC_RES_MAX_PAIRS");
         p->res_max_pairs = getenv("SC_NO_RESIDENT") ? 0 : (env ? strtoull(env, nullptr, 10) : RES_MAX_PAIRS_DEFAULT);
@@ -869,6 +961,8 @@ int upload_tables(sc_prover* p, const uint64_t* const* tables) {
     rp.tmaps = p->d_maps + (size_t)3 * p->T * sizeof(CUtensorMap);
     rp.raw_out = 1;
     rp.seq = epoch;
+    const bool gemm = gemm_round_ok(p, rp.n_pairs, false);
+    p->eager_gemm = gemm;
     for (uint32_t c = 0; c < EAGER_CHUNKS; c++) {
         for (uint32_t j = 0; j < p->T; j++)
             CUDA_TRY(h2d(lease.B, p->tab0[j] + c * chunk_elems * 8, tables[j] + c * chunk_elems * 4, chunk_elems * 32, p->copy_stream));
@@ -877,6 +971,11 @@ int upload_tables(sc_prover* p, const uint64_t* const* tables) {
         rp.tile_base = (uint32_t)(c * (tiles / EAGER_CHUNKS));
         rp.host_out = p->d_eager + (size_t)c * EAGER_SLOT_WORDS;
         rp.host_flag = p->d_eager + (size_t)c * EAGER_SLOT_WORDS + sck::MAX_NPTS * 8;
+        if (gemm) {
+            int rc = launch_gemm_round(p, rp, false, rp.tile_base, tiles / EAGER_CHUNKS, 1 + c, epoch);
+            if (rc) return rc;
+            continue;
+        }
         cudaError_t e;
         switch (p->d + 1) {
             case 1: e = launch_round1_tma<1>(p, rp); break;
@@ -902,6 +1001,19 @@ int sharded_round(sc_prover* p, const uint64_t* r);  // capi_multi.inc
 void host_finish_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
     const uint32_t d = p->d, ns = w->raw_npts;
     hfr::F sums[8], out[8], coeff;
+    if (w->gemm_active) {  // six big integers from the contraction kernels -> P(0..d)
+        hfr::gemm_finish(w->h_gemm, GEMM_LIMBS3, 2, 1, d, out);
+        if (p->n_products == 1) {
+            memcpy(&coeff, p->h_coeffs.data(), 32);
+            for (uint32_t t = 0; t <= d; t++) out[t] = hfr::mul(out[t], coeff);
+        }
+        for (uint32_t t = 0; t <= d; t++) {
+            const hfr::F c = hfr::to_canonical(out[t]);
+            memcpy(p->h_evals + (size_t)t * 8, &out[t], 32);
+            memcpy(p->h_canon + (size_t)t * 8, &c, 32);
+        }
+        return;
+    }
     memcpy(sums, w->h_result, (size_t)ns * 32);
     const bool scale = p->n_products == 1;
     if (scale) memcpy(&coeff, p->h_coeffs.data(), 32);
@@ -1109,6 +1221,7 @@ int resident_collect(sc_prover* p, sc_prover* w, const uint64_t* r) {
     w->raw_npts = d;
     w->used_skip1 = true;
     w->alt_active = true;  // the resident kernel sums at the alternative points
+    w->gemm_active = false;
     host_finish_round(p, w, r);
     memcpy(p->h_prev.data(), p->h_evals, (size_t)(d + 1) * 32);
     w->cur = (w->cur == 1) ? 2 : 1;
@@ -1159,7 +1272,8 @@ int prove_round_issue(sc_prover* p, const uint64_t* r_or_null) {
     if (p->eager_valid && p->round == 1 && !p->comm) {
         // round 1 was summed in EAGER_CHUNKS pieces behind the upload: wait for the last piece, add the pieces, finish
         p->eager_valid = false;
-        volatile uint32_t* flag = p->h_eager + (size_t)(EAGER_CHUNKS - 1) * EAGER_SLOT_WORDS + sck::MAX_NPTS * 8;
+        volatile uint32_t* flag = p->eager_gemm ? p->h_gemm + (size_t)(EAGER_CHUNKS + 1) * gsum::OUT_SLOT_WORDS - 1
+                                                : p->h_eager + (size_t)(EAGER_CHUNKS - 1) * EAGER_SLOT_WORDS + sck::MAX_NPTS * 8;
         SpinWait sw;
         while (*flag != p->eager_epoch) {
             sw.pause();
@@ -1171,18 +1285,28 @@ int prove_round_issue(sc_prover* p, const uint64_t* r_or_null) {
         }
         __sync_synchronize();
         const uint32_t npts = p->d + 1;
-        hfr::F tot[8];
-        memset(tot, 0, sizeof(tot));
-        for (uint32_t c = 0; c < EAGER_CHUNKS; c++)
-            for (uint32_t t = 0; t < npts; t++) {
-                hfr::F x;
-                memcpy(&x, p->h_eager + (size_t)c * EAGER_SLOT_WORDS + t * 8, 32);
-                tot[t] = hfr::add(tot[t], x);
-            }
-        memcpy(p->h_result, tot, (size_t)npts * 32);
+        if (p->eager_gemm) {  // add the chunks' integers up in slot 0
+            memset(p->h_gemm, 0, (size_t)GEMM_NB3 * GEMM_LIMBS3 * 4);
+            for (uint32_t c = 0; c < EAGER_CHUNKS; c++)
+                for (uint32_t i = 0; i < GEMM_NB3; i++)
+                    hfr::add_limbs(p->h_gemm + (size_t)i * GEMM_LIMBS3, p->h_gemm + (size_t)(1 + c) * gsum::OUT_SLOT_WORDS + (size_t)i * GEMM_LIMBS3, GEMM_LIMBS3);
+            p->gemm_active = true;
+            p->gemm_rounds++;
+        } else {
+            hfr::F tot[8];
+            memset(tot, 0, sizeof(tot));
+            for (uint32_t c = 0; c < EAGER_CHUNKS; c++)
+                for (uint32_t t = 0; t < npts; t++) {
+                    hfr::F x;
+                    memcpy(&x, p->h_eager + (size_t)c * EAGER_SLOT_WORDS + t * 8, 32);
+                    tot[t] = hfr::add(tot[t], x);
+                }
+            memcpy(p->h_result, tot, (size_t)npts * 32);
+            p->gemm_active = false;
+            p->alt_active = true;  // the chunks were summed by round1_tma_kernel
+        }
         p->raw_npts = npts;
         p->used_skip1 = false;
-        p->alt_active = true;  // the chunks were summed by round1_tma_kernel
         host_finish_round(p, p, nullptr);
         memcpy(p->h_prev.data(), p->h_evals, (size_t)npts * 32);
         p->out_evals = p->d_evals;
@@ -1229,7 +1353,7 @@ int prove_round_collect(sc_prover* p, const uint64_t* r_or_null, bool sync_out) 
     if (p->direct_active) {
         // the last block wrote the message into mapped pinned memory and then the flag: spin instead of copy + sync
         sc_prover* w = (p->comm && p->wait_on) ? p->wait_on : p;
-        volatile uint32_t* flag = w->h_result + (size_t)(p->d + 1) * 16;
+        volatile uint32_t* flag = w->gemm_active ? w->h_gemm + gsum::OUT_SLOT_WORDS - 1 : w->h_result + (size_t)(p->d + 1) * 16;
         const uint32_t want = w->seq;
         SpinWait sw;
         while (*flag != want) {
@@ -1510,6 +1634,7 @@ int sc_prover_reset(sc_prover* p) {
     p->launches = 0;
     p->tc_rounds = 0;
     p->res_rounds = 0;
+    p->gemm_rounds = 0;
     p->eager_valid = false;  // a pre-computed first round belongs to the proof that follows its upload only
     p->switched = false;
     if (p->comm) comm_clear_error(p);  // a timed-out exchange invalidated the previous proof, not the communicator
@@ -1676,6 +1801,7 @@ uint32_t sc_prover_round_times_ms(const sc_prover* p, float* out, uint32_t cap) 
 uint64_t sc_prover_launch_count(const sc_prover* p) { return p ? lead(p)->launches : 0; }
 uint64_t sc_prover_tc_round_count(const sc_prover* p) { return p ? lead(p)->tc_rounds : 0; }
 uint64_t sc_prover_resident_round_count(const sc_prover* p) { return p ? lead(p)->res_rounds : 0; }
+uint64_t sc_prover_gemm_round_count(const sc_prover* p) { return p ? lead(p)->gemm_rounds : 0; }
 
 void sc_release_cached_memory(void) {
     std::lock_guard<std::mutex> lk(g_cache_mu);

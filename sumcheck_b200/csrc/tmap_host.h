@@ -44,4 +44,18 @@ inline bool make_table_map(CUtensorMap* out, const void* base, uint64_t rows, ui
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// rows x 64 bytes (one PAIR of field elements per row) with SWIZZLE_64B: what lands in shared memory is the MN-major operand of
+// the tensor-core contraction (gemm_sum.cuh), the pair index being its K dimension.
+inline bool make_pair_map(CUtensorMap* out, const void* base, uint64_t rows, uint32_t box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || rows == 0 || rows >= ((uint64_t)1 << 31) || ((uintptr_t)base & 15)) return false;
+    const cuuint64_t dims[2] = {16, rows};
+    const cuuint64_t strides[1] = {64};
+    const cuuint32_t box[2] = {16, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace tmaph
