@@ -11,7 +11,7 @@ namespace gsum {
 cudaError_t init_constants() { return fr::fr_init_constants(); }  // this TU's copy of the __constant__ modulus
 
 #ifndef SC_GEMM_G1
-#define SC_GEMM_G1 4  // compute groups per CTA, round 1
+#define SC_GEMM_G1 3  // compute groups per CTA, round 1 (three: 144 registers per thread leave room for the next item's pairs)
 #endif
 #ifndef SC_GEMM_GF
 #define SC_GEMM_GF 3  // compute groups per CTA, fold rounds (shared memory and tensor memory allow three)
@@ -64,7 +64,7 @@ cudaError_t launch_fold(const Params& P, int sms, cudaStream_t stream) {
     const size_t smem = FoldSmem<GF>::BYTES;
     cudaError_t e = prepare<2>(gemm_fold_kernel<GF>, smem);
     if (e != cudaSuccess) return e;
-    gemm_fold_kernel<GF><<<grid_for(P.items, GF, sms), GF * 128 + 64, smem, stream>>>(P);
+    gemm_fold_kernel<GF><<<grid_for(P.items, GF, sms), GF * 128 + 96, smem, stream>>>(P);
     return cudaGetLastError();
 }
 

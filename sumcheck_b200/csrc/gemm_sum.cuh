@@ -32,6 +32,25 @@ constexpr uint32_t TILE = 128;               // pairs per work item = threads pe
 constexpr uint32_t OUT_SLOT_WORDS = 512;     // mapped result slot: NB * OUT_LIMBS words, sequence flag in the last word
 constexpr uint32_t MAX_ITEMS_PER_CTA = 256;  // 4 K-steps of 32 pairs each: every s32 accumulator stays below 2^31
 constexpr uint32_t TOT_STRIDE = 128;         // u64 totals per block pair (>= number of anti-diagonals)
+constexpr uint32_t MAX_PRODUCTS = 32;        // the CSR of the product list is cached in shared memory (3 entries per product)
+
+// The product list as the kernels use it, in shared memory: a dependent chain of global loads (offsets -> indices -> table
+// pointer) per work item costs the single producer thread ~1700 cycles per table tile (measured) and made it the bottleneck.
+struct CsrCache {
+    uint32_t idx[3 * MAX_PRODUCTS];          // table index of CSR entry 3k + j
+    uint32_t first[3 * MAX_PRODUCTS];        // 1 where the entry is the first use of its table (that use stores the fold)
+    const uint32_t* in[3 * MAX_PRODUCTS];    // tab_in of the entry
+    uint32_t* out[3 * MAX_PRODUCTS];         // tab_out of the entry (fold rounds)
+};
+__device__ __forceinline__ void load_csr(CsrCache& c, const sck::RoundParams& p, bool fold) {
+    for (uint32_t e = threadIdx.x; e < 3 * p.n_products; e += blockDim.x) {
+        const uint32_t jj = p.prod_offsets[e / 3] + e % 3, idx = p.prod_indices[jj];
+        c.idx[e] = idx;
+        c.first[e] = p.prod_first[jj];
+        c.in[e] = p.tab_in[idx];
+        c.out[e] = fold ? p.tab_out[idx] : nullptr;
+    }
+}
 
 struct Params {
     sck::RoundParams rp;          // tables, CSR, tmaps (fold rounds: 128-byte rows), n_pairs, tile_base, host_out/host_flag/seq, counter, r
@@ -39,6 +58,14 @@ struct Params {
     unsigned long long* totals;   // [NB][TOT_STRIDE], zero before the launch; the publishing launch leaves it zero again
     uint32_t publish;             // 0: only add into totals (a round split over several launches), 1: the last CTA publishes
     uint32_t items;               // work items (tile, product) of this launch
+    long long* prof;              // SC_GEMM_PROF=1: [16] cycle counters summed over the CTAs (waits per role), else null
+};
+
+struct ProfTimer {  // accumulates clock64 intervals of one thread; flushed with one atomicAdd per counter at the end
+    long long acc = 0, t0 = 0;
+    __device__ __forceinline__ void start(bool on) { if (on) t0 = clock64(); }
+    __device__ __forceinline__ void stop(bool on) { if (on) acc += clock64() - t0; }
+    __device__ __forceinline__ void flush(long long* prof, int slot) { if (prof) atomicAdd((unsigned long long*)prof + slot, (unsigned long long)acc); }
 };
 
 // ---- MN-major operand descriptors (checked by tools/microbench/gemmsum.cu) ------------------------------------------------------
@@ -192,14 +219,25 @@ __device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool
     __threadfence();
     if (tid == 0) *P.rp.counter = 0;
     if (!P.publish) return;
+    // the grid's totals into shared memory with independent loads (a dependent chain of 95 L2 round trips per integer cost
+    // ~25 us per launch), leaving the global copy zero for the next launch
+    unsigned long long* s_tot = reinterpret_cast<unsigned long long*>(s_E);  // [NB3][96]
+    __syncthreads();
+    for (uint32_t i = tid; i < NB3 * 96; i += blockDim.x) {
+        const uint32_t bp = i / 96, k = i % 96;
+        unsigned long long v = 0;
+        if (k < DIAG3) {
+            v = __ldcg(P.totals + bp * TOT_STRIDE + k);
+            P.totals[bp * TOT_STRIDE + k] = 0;
+        }
+        s_tot[i] = v;
+    }
+    __syncthreads();
     if (tid < NB3) {  // Z = sum_k 2^(8k) totals[k]: byte-serial carry into OUT_LIMBS3 limbs
         unsigned long long acc = 0;
         uint32_t limb = 0;
         for (uint32_t k = 0; k < OUT_LIMBS3 * 4; k++) {
-            if (k < DIAG3) {
-                acc += __ldcg(P.totals + tid * TOT_STRIDE + k);
-                P.totals[tid * TOT_STRIDE + k] = 0;
-            }
+            if (k < DIAG3) acc += s_tot[tid * 96 + k];
             limb |= (uint32_t)(acc & 0xffu) << (8 * (k & 3u));
             acc >>= 8;
             if ((k & 3u) == 3u) {
@@ -227,10 +265,12 @@ __global__ void __launch_bounds__(G * 128 + 64, 1) gemm_round1_kernel(const Para
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t y_full[G][2], y_empty[G][2], x_full[G], x_empty[G];
     __shared__ uint32_t s_tmem;
-    __shared__ uint32_t s_E[2 * NB3 * 96];
+    __shared__ __align__(8) uint32_t s_E[2 * NB3 * 96];
     __shared__ bool s_last;
+    __shared__ CsrCache s_csr;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const sck::RoundParams& p = P.rp;
+    load_csr(s_csr, p, false);
     if (tid == 0) {
         if (tcf::smem_u32(smem) & 1023u) __trap();
         for (int g = 0; g < G; g++) {
@@ -259,16 +299,27 @@ __global__ void __launch_bounds__(G * 128 + 64, 1) gemm_round1_kernel(const Para
         const uint32_t g = warp >> 2, t = tid & 127u;
         uint8_t* const base = smem + (size_t)g * R1Smem<G>::GROUP;
         const uint32_t n_items = items_of(g);
-        for (uint32_t n = 0; n < n_items; n++) {
+        const bool one_product = p.n_products == 1;
+        Fr a0, b0, a1, b1, na0, nb0, na1, nb1;
+        // this thread's pairs of the product's first two tables for item n (the next item's are requested before this item's
+        // products are computed: a group always has 16 KiB of loads in flight)
+        auto fetch = [&](uint32_t n, Fr& x0, Fr& y0, Fr& x1, Fr& y1) {
             const uint32_t w = blockIdx.x * G + g + n * stride;
-            const uint32_t k = w % p.n_products, tile = p.tile_base + w / p.n_products;
-            const uint32_t j0 = p.prod_offsets[k];
+            const uint32_t k = one_product ? 0u : w % p.n_products, tile = p.tile_base + (one_product ? w : w / p.n_products);
             const unsigned long long b = (unsigned long long)tile * TILE + t;
-            const uint32_t* s0 = p.tab_in[p.prod_indices[j0]] + b * 16;
-            const uint32_t* s1 = p.tab_in[p.prod_indices[j0 + 1]] + b * 16;
-            const Fr a0 = fr::load_stream(s0), b0 = fr::load_stream(s0 + 8), a1 = fr::load_stream(s1), b1 = fr::load_stream(s1 + 8);
+            const uint32_t* s0 = s_csr.in[3 * k] + b * 16;
+            const uint32_t* s1 = s_csr.in[3 * k + 1] + b * 16;
+            x0 = fr::load_stream(s0);
+            y0 = fr::load_stream(s0 + 8);
+            x1 = fr::load_stream(s1);
+            y1 = fr::load_stream(s1 + 8);
+        };
+        if (n_items) fetch(0, a0, b0, a1, b1);
+        for (uint32_t n = 0; n < n_items; n++) {
+            if (n + 1 < n_items) fetch(n + 1, na0, nb0, na1, nb1);
             if (n > 0) tcf::mbar_wait(&x_empty[g], (n - 1) & 1u);  // the contraction of item n-1 has read the X operand
             products_to_smem(a0, b0, a1, b1, base + R1Smem<G>::XA, base + R1Smem<G>::XQ, t);
+            a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
             tcf::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tcf::mbar_arrive(&x_full[g]);
@@ -288,7 +339,7 @@ __global__ void __launch_bounds__(G * 128 + 64, 1) gemm_round1_kernel(const Para
                     if (n >= 2) tcf::mbar_wait(&y_empty[g][s], ((n >> 1) - 1u) & 1u);
                     const uint32_t w = blockIdx.x * G + g + n * stride;
                     const uint32_t k = w % p.n_products, tile = p.tile_base + w / p.n_products;
-                    const uint32_t idx = p.prod_indices[p.prod_offsets[k] + 2];
+                    const uint32_t idx = s_csr.idx[3 * k + 2];
                     tcf::mbar_expect_tx(&y_full[g][s], 8192);
                     tcf::tma_load_tile(smem + (size_t)g * R1Smem<G>::GROUP + (s ? R1Smem<G>::Y1 : R1Smem<G>::Y0), (const uint8_t*)P.ymaps + (size_t)idx * 128,
                                        &y_full[g][s], tile * TILE);
@@ -329,10 +380,14 @@ __global__ void __launch_bounds__(G * 128 + 64, 1) gemm_round1_kernel(const Para
 }
 
 // ================================================================================================ fold rounds, degree 3
-// Every table tile (128 rows x 128 bytes = old[4b..4b+3]) goes HBM -> shared memory by TMA into a ring shared by the groups;
-// P0 issues the fix_variables MMAs (tc_fold.cuh) into the owning group's accumulator (two per group, alternating); the group's
-// thread t reads out new[2b], new[2b+1] of pair b = tile * 128 + t, stores them (the folded table) and, once it holds the pairs
-// of the product's first two tables, writes the three plain products; the folded pair of the third table is the Y operand.
+// Every table tile (128 rows x 128 bytes = old[4b..4b+3]) goes HBM -> shared memory by TMA into a ring shared by the groups
+// (warp W_TMA); warp W_FOLD issues the fix_variables MMAs (tc_fold.cuh) into the owning group's accumulator (two per group,
+// alternating); the group's thread t reads out new[2b], new[2b+1] of pair b = tile * 128 + t, stores them (the folded table)
+// and, once it holds the pairs of the product's first two tables, writes the three plain products; the folded pair of the
+// third table is the Y operand; warp W_SUM issues the contraction MMAs.  Each producer warp walks the same sequence of units
+// (item n, multiplicand j, group g) — g innermost, so consecutive units belong to different groups — and never computes
+// anything but a ring slot and a barrier phase (a producer that also chased the product list through global memory cost
+// ~1700 cycles per unit and starved every group: measured).
 template <int G>
 struct FoldSmem {
     static constexpr uint32_t RING_SLOTS = 6;
@@ -342,34 +397,46 @@ struct FoldSmem {
     static constexpr size_t BYTES = (size_t)BMAT + tcf::BMAT_BYTES;
 };
 
-// the order in which P0 walks the (item n, multiplicand j, group g) units of a CTA: j inside n, g innermost, so that
-// consecutive units belong to different groups and a group's two accumulators are rarely both busy
+// Work split of one CTA: group g owns the items w = blockIdx.x * G + g + n * stride, n < n_items(g).  n_items is non-increasing
+// in g and differs by at most one between groups, so all G groups take part in every step n < n_min and the first `rem` groups
+// in the (possibly) partial last step n = n_min.  Unit (n, j, g) is the u-th of the CTA with u = 3 G n + j * groups(n) + g.
 template <int G>
-struct UnitCursor {
-    uint32_t n = 0, j = 0, g = 0;
-    const uint32_t* n_items;
-    __device__ __forceinline__ explicit UnitCursor(const uint32_t* ni) : n_items(ni) { settle(); }
-    __device__ __forceinline__ void settle() {
-        while (n_items[g] <= n) {  // the caller never walks past the last unit
-            if (++g == G) { g = 0; if (++j == 3) { j = 0; n++; } }
+struct Split {
+    uint32_t n_min, rem, stride, first;
+    __device__ __forceinline__ Split(uint32_t items) {
+        stride = gridDim.x * G;
+        first = blockIdx.x * G;
+        const uint32_t last_g = first + G - 1;
+        n_min = last_g < items ? (items - last_g + stride - 1) / stride : 0u;
+        rem = 0;
+#pragma unroll
+        for (int g = 0; g < G - 1; g++) {
+            const uint32_t f = first + g;
+            const uint32_t ni = f < items ? (items - f + stride - 1) / stride : 0u;
+            rem += ni > n_min ? 1u : 0u;
         }
     }
-    __device__ __forceinline__ void next() {
-        if (++g == G) { g = 0; if (++j == 3) { j = 0; n++; } }
-    }
+    __device__ __forceinline__ uint32_t n_items(uint32_t g) const { return n_min + (g < rem ? 1u : 0u); }
+    __device__ __forceinline__ uint32_t steps() const { return n_min + (rem ? 1u : 0u); }
+    __device__ __forceinline__ uint32_t groups(uint32_t n) const { return n < n_min ? (uint32_t)G : rem; }
+    __device__ __forceinline__ uint32_t unit(uint32_t n, uint32_t j, uint32_t g) const { return 3u * G * n + j * groups(n) + g; }
+    __device__ __forceinline__ uint32_t item(uint32_t n, uint32_t g) const { return first + g + n * stride; }
 };
 
 template <int G>
-__global__ void __launch_bounds__(G * 128 + 64, 1) gemm_fold_kernel(const Params P) {
+__global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params P) {
     using L = FoldSmem<G>;
     constexpr uint32_t R = L::RING_SLOTS;
+    constexpr uint32_t W_TMA = G * 4, W_FOLD = G * 4 + 1, W_SUM = G * 4 + 2;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t slot_full[R], slot_empty[R], acc_full[G][2], acc_empty[G][2], x_full[G], x_empty[G];
     __shared__ uint32_t s_tmem;
-    __shared__ uint32_t s_E[2 * NB3 * 96];
+    __shared__ __align__(8) uint32_t s_E[2 * NB3 * 96];
     __shared__ bool s_last;
+    __shared__ CsrCache s_csr;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const sck::RoundParams& p = P.rp;
+    load_csr(s_csr, p, true);
     uint8_t* const bmat = smem + L::BMAT;
     if (tid == 0) {
         if (tcf::smem_u32(smem) & 1023u) __trap();
@@ -399,27 +466,30 @@ __global__ void __launch_bounds__(G * 128 + 64, 1) gemm_fold_kernel(const Params
     __syncthreads();
     tcf::tc_fence_after();
     const uint32_t tmem = s_tmem;
-    const uint32_t stride = gridDim.x * G;
-    auto items_of = [&](uint32_t g) {
-        const uint32_t first = blockIdx.x * G + g;
-        return first < P.items ? (P.items - first + stride - 1) / stride : 0u;
-    };
+    const Split<G> sp(P.items);
+    const bool one_product = p.n_products == 1;
+    const bool pf = P.prof != nullptr && lane == 0;
     if (warp < G * 4) {
         // ---------------------------------------------------------------------------------------------------- compute group
         const uint32_t g = warp >> 2, t = tid & 127u;
         uint8_t* const base = smem + L::GROUPS + (size_t)g * L::GROUP;
         const uint32_t lane_taddr = tmem + 128u + g * 128u + (((warp & 3u) * 32u) << 16);
-        const uint32_t n_items = items_of(g);
+        const uint32_t n_items = sp.n_items(g);
+        ProfTimer t_acc, t_x, t_all;
+        t_all.start(pf);
         for (uint32_t n = 0; n < n_items; n++) {
-            const uint32_t w = blockIdx.x * G + g + n * stride;
-            const uint32_t k = w % p.n_products, tile = p.tile_base + w / p.n_products;
-            const uint32_t j0 = p.prod_offsets[k];
+            const uint32_t w = sp.item(n, g);
+            const uint32_t k = one_product ? 0u : w % p.n_products, tile = p.tile_base + (one_product ? w : w / p.n_products);
             const unsigned long long b = (unsigned long long)tile * TILE + t;
             Fr e0, o0;
 #pragma unroll
             for (uint32_t j = 0; j < 3; j++) {
                 const uint32_t q = 3 * n + j, a = q & 1u;
+                t_acc.start(pf);
                 tcf::mbar_wait(&acc_full[g][a], (q >> 1) & 1u);
+                t_acc.stop(pf);
+                // the fold MMAs of this unit have completed: its ring slot is free again
+                if ((warp & 3u) == 0 && lane == 0) tcf::mbar_arrive(&slot_empty[sp.unit(n, j, g) % R]);
                 tcf::tc_fence_after();
                 uint32_t S[32];
                 tcf::tmem_ld32(lane_taddr + a * 64u, S);
@@ -431,9 +501,8 @@ __global__ void __launch_bounds__(G * 128 + 64, 1) gemm_fold_kernel(const Params
                 __syncwarp();
                 if (lane == 0) tcf::mbar_arrive(&acc_empty[g][a]);
                 const Fr v1 = tcf::columns_to_fr(S);
-                const uint32_t jj = j0 + j;
-                if (p.write_fold && p.prod_first[jj]) {
-                    uint32_t* dst = p.tab_out[p.prod_indices[jj]] + b * 16;
+                if (s_csr.first[3 * k + j]) {
+                    uint32_t* dst = s_csr.out[3 * k + j] + b * 16;
                     fr::store(dst, v0);
                     fr::store(dst + 8, v1);
                 }
@@ -441,7 +510,9 @@ __global__ void __launch_bounds__(G * 128 + 64, 1) gemm_fold_kernel(const Params
                     e0 = v0;
                     o0 = v1;
                 } else if (j == 1) {
+                    t_x.start(pf);
                     if (n > 0) tcf::mbar_wait(&x_empty[g], (n - 1) & 1u);  // the contraction of item n-1 has read X and Y
+                    t_x.stop(pf);
                     products_to_smem(e0, o0, v0, v1, base + L::XA, base + L::XQ, t);
                 } else {
                     uint32_t y[16];
@@ -457,79 +528,104 @@ __global__ void __launch_bounds__(G * 128 + 64, 1) gemm_fold_kernel(const Params
             __syncwarp();
             if (lane == 0) tcf::mbar_arrive(&x_full[g]);
         }
-    } else if (warp == G * 4) {
-        // ---------------------------------------------------------------------------------------------------- P0: TMA + fold MMAs
+        t_all.stop(pf);
+        if (pf) { t_acc.flush(P.prof, 0); t_x.flush(P.prof, 1); t_all.flush(P.prof, 2); }
+    } else if (warp == W_TMA) {
+        // ---------------------------------------------------------------------------------------------------- TMA: table tiles into the ring
         if (lane == 0) {
-            uint32_t n_items[G], U = 0;
-            for (int g = 0; g < G; g++) {
-                n_items[g] = items_of(g);
-                U += 3 * n_items[g];
+            ProfTimer t_se, t_all;
+            t_all.start(pf);
+            uint32_t u = 0;
+            const uint32_t steps = sp.steps();
+            for (uint32_t n = 0; n < steps; n++) {
+                const uint32_t ng = sp.groups(n);
+#pragma unroll
+                for (uint32_t j = 0; j < 3; j++)
+#pragma unroll
+                    for (uint32_t g = 0; g < (uint32_t)G; g++) {
+                        if (g >= ng) continue;
+                        const uint32_t slot = u % R;
+                        t_se.start(pf);
+                        if (u >= R) tcf::mbar_wait(&slot_empty[slot], ((u / R) - 1u) & 1u);
+                        t_se.stop(pf);
+                        const uint32_t w = sp.item(n, g);
+                        const uint32_t k = one_product ? 0u : w % p.n_products, tile = p.tile_base + (one_product ? w : w / p.n_products);
+                        tcf::mbar_expect_tx(&slot_full[slot], tcf::TILE_BYTES);
+                        tcf::tma_load_tile(smem + (size_t)slot * tcf::TILE_BYTES, (const uint8_t*)p.tmaps + (size_t)s_csr.idx[3 * k + j] * 128, &slot_full[slot],
+                                           tile * TILE);
+                        u++;
+                    }
             }
-            if (U) {
-                UnitCursor<G> ct(n_items), cm(n_items);
-                const uint32_t ring = tcf::smem_u32(smem), bmat_smem = tcf::smem_u32(bmat);
-                uint32_t u_tma = 0;
-                auto issue_tma = [&](uint32_t slot) {
-                    const uint32_t w = blockIdx.x * G + ct.g + ct.n * stride;
-                    const uint32_t k = w % p.n_products, tile = p.tile_base + w / p.n_products;
-                    const uint32_t idx = p.prod_indices[p.prod_offsets[k] + ct.j];
-                    tcf::mbar_expect_tx(&slot_full[slot], tcf::TILE_BYTES);
-                    tcf::tma_load_tile(smem + (size_t)slot * tcf::TILE_BYTES, (const uint8_t*)p.tmaps + (size_t)idx * 128, &slot_full[slot], tile * TILE);
-                    u_tma++;
-                    if (u_tma < U) {
-                        ct.next();
-                        ct.settle();
+            t_all.stop(pf);
+            if (pf) { t_se.flush(P.prof, 5); t_all.flush(P.prof, 11); }
+        }
+    } else if (warp == W_FOLD) {
+        // ---------------------------------------------------------------------------------------------------- fix_variables MMAs
+        if (lane == 0) {
+            ProfTimer t_sf, t_ae, t_all, t_mma;
+            t_all.start(pf);
+            const uint32_t ring = tcf::smem_u32(smem), bmat_smem = tcf::smem_u32(bmat);
+            uint32_t u = 0;
+            const uint32_t steps = sp.steps();
+            for (uint32_t n = 0; n < steps; n++) {
+                const uint32_t ng = sp.groups(n);
+#pragma unroll
+                for (uint32_t j = 0; j < 3; j++)
+#pragma unroll
+                    for (uint32_t g = 0; g < (uint32_t)G; g++) {
+                        if (g >= ng) continue;
+                        const uint32_t slot = u % R, q = 3 * n + j, a = q & 1u;
+                        t_sf.start(pf);
+                        tcf::mbar_wait(&slot_full[slot], (u / R) & 1u);
+                        t_sf.stop(pf);
+                        t_ae.start(pf);
+                        if (q >= 2) tcf::mbar_wait(&acc_empty[g][a], ((q >> 1) - 1u) & 1u);
+                        t_ae.stop(pf);
+                        tcf::tc_fence_after();
+                        t_mma.start(pf);
+                        tcf::issue_fold_mma(ring + slot * tcf::TILE_BYTES, bmat_smem, tmem + 128u + g * 128u + a * 64u);
+                        tcf::umma_commit(&acc_full[g][a]);
+                        t_mma.stop(pf);
+                        u++;
                     }
-                };
-                while (u_tma < R && u_tma < U) issue_tma(u_tma);
-                for (uint32_t u = 0; u < U; u++) {
-                    const uint32_t slot = u % R;
-                    tcf::mbar_wait(&slot_full[slot], (u / R) & 1u);
-                    const uint32_t q = 3 * cm.n + cm.j, a = q & 1u;
-                    if (q >= 2) tcf::mbar_wait(&acc_empty[cm.g][a], ((q >> 1) - 1u) & 1u);
-                    tcf::tc_fence_after();
-                    tcf::issue_fold_mma(ring + slot * tcf::TILE_BYTES, bmat_smem, tmem + 128u + cm.g * 128u + a * 64u);
-                    tcf::umma_commit(&acc_full[cm.g][a]);
-                    tcf::umma_commit(&slot_empty[slot]);
-                    if (u >= 1 && u_tma < U) {  // refill the slot of the previous unit: its MMAs have (all but) completed
-                        const uint32_t ps = (u - 1) % R;
-                        tcf::mbar_wait(&slot_empty[ps], ((u - 1) / R) & 1u);
-                        issue_tma(ps);
-                    }
-                    if (u + 1 < U) {
-                        cm.next();
-                        cm.settle();
-                    }
-                }
             }
+            t_all.stop(pf);
+            if (pf) { t_sf.flush(P.prof, 3); t_ae.flush(P.prof, 4); t_all.flush(P.prof, 6); t_mma.flush(P.prof, 8); }
         }
     } else {
-        // ---------------------------------------------------------------------------------------------------- P1: contraction MMAs
+        // ---------------------------------------------------------------------------------------------------- contraction MMAs
         if (lane == 0) {
-            uint32_t n_items[G], max_items = 0;
-            for (int g = 0; g < G; g++) {
-                n_items[g] = items_of(g);
-                max_items = n_items[g] > max_items ? n_items[g] : max_items;
-            }
+            ProfTimer t_xf, t_iss;
             uint32_t acc = 0;
-            for (uint32_t n = 0; n < max_items; n++)
-                for (int g = 0; g < G; g++) {
-                    if (n >= n_items[g]) continue;
+            const uint32_t steps = sp.steps();
+            for (uint32_t n = 0; n < steps; n++) {
+                const uint32_t ng = sp.groups(n);
+#pragma unroll
+                for (uint32_t g = 0; g < (uint32_t)G; g++) {
+                    if (g >= ng) continue;
                     const uint32_t gb = tcf::smem_u32(smem + L::GROUPS + (size_t)g * L::GROUP);
+                    t_xf.start(pf);
                     tcf::mbar_wait(&x_full[g], n & 1u);
+                    t_xf.stop(pf);
                     tcf::tc_fence_after();
+                    t_iss.start(pf);
                     issue_contraction(gb + L::XA, gb + L::XQ, gb + L::Y, tmem, acc);
                     acc = 1;
                     tcf::umma_commit(&x_empty[g]);
+                    t_iss.stop(pf);
                 }
-            for (int g = 0; g < G; g++)
-                if (n_items[g]) tcf::mbar_wait(&x_empty[g], (n_items[g] - 1) & 1u);
+            }
+            // every MMA has completed once the last commit of every group has arrived
+#pragma unroll
+            for (uint32_t g = 0; g < (uint32_t)G; g++)
+                if (sp.n_items(g)) tcf::mbar_wait(&x_empty[g], (sp.n_items(g) - 1) & 1u);
+            if (pf) { t_xf.flush(P.prof, 7); t_iss.flush(P.prof, 10); }
         }
     }
     __syncwarp();
     tcf::tc_fence_before();
     __syncthreads();
-    epilogue3(P, tmem, items_of(0) > 0, s_E, &s_last);
+    epilogue3(P, tmem, sp.n_items(0) > 0, s_E, &s_last);
     __syncthreads();
     if (warp == 0) tcf::tmem_dealloc(tmem, 512);
 }

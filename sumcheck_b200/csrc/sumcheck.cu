@@ -431,7 +431,7 @@ constexpr uint32_t GEMM_LIMBS3 = gsum::OUT_LIMBS3, GEMM_NB3 = gsum::NB3;
 
 // May this round (n_pairs output pairs; fold = rounds >= 2) run on the contraction kernels?
 bool gemm_round_ok(const sc_prover* p, unsigned long long n_pairs, bool fold) {
-    if (!p->gemm_shape || p->comm || p->is_shard || !p->host_post || !p->direct_results) return false;
+    if (!p->gemm_shape || p->comm || p->is_shard || !p->host_post || !p->direct_results || p->n_products > gsum::MAX_PRODUCTS) return false;
     if (p->n_products > 1)
         for (uint32_t k = 0; k < p->n_products; k++)
             if (!p->h_scaled[k]) return false;  // a coefficient that is not inside a table would have to be applied per product
@@ -463,8 +463,24 @@ int launch_gemm_round(sc_prover* p, const sck::RoundParams& rp, bool fold, unsig
         G.items = (uint32_t)(take * p->n_products);
         G.publish = (t + take == n_tiles) ? 1u : 0u;
         p->launches++;
+        static const bool prof = getenv("SC_GEMM_PROF") != nullptr;  // debugging aid: wait cycles per role, printed per launch
+        long long* d_prof = nullptr;
+        if (prof) {
+            cudaMalloc(&d_prof, 16 * sizeof(long long));
+            cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), p->stream);
+            G.prof = d_prof;
+        }
         cudaError_t e = fold ? gsum::launch_fold(G, sms, p->stream) : gsum::launch_round1(G, sms, p->stream);
         if (e != cudaSuccess) return fail(SC_ERR_CUDA, "contraction kernel launch: %s", cudaGetErrorString(e));
+        if (prof) {
+            long long h[16];
+            cudaStreamSynchronize(p->stream);
+            cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+            cudaFree(d_prof);
+            const double ctas = (double)((G.items + 2) / 3 < (uint32_t)sms ? (G.items + 2) / 3 : (uint32_t)sms), cw = ctas * 12;
+            fprintf(stderr, "gemm %s items %u: per compute warp: total %.0f, wait acc_full %.0f, wait x_empty %.0f | fold warp per CTA: total %.0f, wait slot_full %.0f, acc_empty %.0f, mma issue + commit %.0f | TMA warp: total %.0f, wait slot_empty %.0f | sum warp: wait x_full %.0f, issue %.0f\n",
+                    fold ? "fold" : "round1", G.items, h[2] / cw, h[0] / cw, h[1] / cw, h[6] / ctas, h[3] / ctas, h[4] / ctas, h[8] / ctas, h[11] / ctas, h[5] / ctas, h[7] / ctas, h[10] / ctas);
+        }
     }
     return SC_OK;
 }
