@@ -255,7 +255,8 @@ def bench_ml(args, cfg, nv, dev):
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     ms_step = ev[0].elapsed_time(ev[args.steps]) / args.steps
     launches = st.launch_count()
-    n_tc, n_res = st.tc_round_count(), st.resident_round_count()
+    n_tc, n_res, n_gemm = st.tc_round_count(), st.resident_round_count(), st.gemm_round_count()
+    gemm = n_gemm > 0  # degree-3 products: the sum over the hypercube runs as a tensor-core contraction (csrc/gemm_sum.cuh)
     # per-round kernel times (CUDA events on the launching stream) from extra, separately instrumented steps
     round_ms = np.zeros(nv, dtype=np.float64)
     st.set_timing(True)
@@ -300,7 +301,9 @@ def bench_ml(args, cfg, nv, dev):
     if tc_rounds:
         dom_bytes = sum(algorithmic_bytes(nv, T, i) for i in tc_rounds)
         dom_ms = float(sum(round_ms[i - 1] for i in tc_rounds))
-        dom_name = f"sck::round_tc_kernel<{d}> (TMA + tcgen05.mma fold fused with the sum), rounds 2..{1 + n_tc} aggregated"
+        dom_name = (f"gsum::gemm_fold_kernel<3> (TMA + tcgen05.mma fix_variables, three plain products per pair, tcgen05.mma contraction over the "
+                    f"pairs), rounds 2..{1 + n_tc} aggregated") if gemm else \
+                   f"sck::round_tc_kernel<{d}> (TMA + tcgen05.mma fold fused with the sum), rounds 2..{1 + n_tc} aggregated"
     else:  # small configs: everything after round 1 is the resident launch
         dom_bytes = sum(algorithmic_bytes(nv, T, i) for i in range(2, nv + 1))
         dom_ms = float(round_ms[1:].sum())
@@ -318,13 +321,14 @@ def bench_ml(args, cfg, nv, dev):
                    "median_ms_per_step": median(step_ms), "first_prover_init_ms": first_init_ms, "proofs_per_s": 1e3 / ms_step,
                    "hypercube_points_per_s": N / (ms_step * 1e-3), "kernel_ms_per_step": float(round_ms.sum()),
                    "round_ms": [round(float(x), 4) for x in round_ms],
-                   "rounds": {"round1_tma_kernel": 1, "round_tc_kernel": int(n_tc), "resident_kernel (one launch)": int(n_res)}},
+                   "rounds": ({"gemm_round1_kernel": 1, "gemm_fold_kernel": int(n_tc), "resident_kernel (one launch)": int(n_res)} if gemm else
+                              {"round1_tma_kernel": 1, "round_tc_kernel": int(n_tc), "resident_kernel (one launch)": int(n_res)})},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                      "kernel": dom_name, "algorithmic_bytes": dom_bytes, "kernel_ms": dom_ms, "peak_source": peak_src,
                      "whole_proof": {"algorithmic_bytes": total_bytes, "achieved": total_bytes / (ms_step * 1e-3) / 1e9,
                                      "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak,
                                      "frac_of_8TBps_nominal": total_bytes / (ms_step * 1e-3) / 8e12},
-                     "round1": {"kernel": f"sck::round1_tma_kernel<{d + 1}>", "achieved": algorithmic_bytes(nv, T, 1) / (round_ms[0] * 1e-3) / 1e9,
+                     "round1": {"kernel": "gsum::gemm_round1_kernel<3>" if gemm else f"sck::round1_tma_kernel<{d + 1}>", "achieved": algorithmic_bytes(nv, T, 1) / (round_ms[0] * 1e-3) / 1e9,
                                 "frac": algorithmic_bytes(nv, T, 1) / (round_ms[0] * 1e-3) / 1e9 / peak},
                      "resident_rounds_ms": res_ms,
                      "note": "traffic: see profiles/ (ncu dram bytes per launch); not re-measured inside bench.py"},

@@ -176,7 +176,8 @@ __device__ __forceinline__ void issue_contraction(uint32_t xa_smem, uint32_t xq_
 constexpr uint32_t NB3 = 6, DIAG3 = 95, OUT_LIMBS3 = 26;
 
 // s_E: [2][NB3 * 96] (low / high 16-bit halves of the accumulators, summed as u32).  Called by the whole CTA; warps 0..3 read TMEM.
-__device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool has_work, uint32_t* s_E, bool* s_last) {
+// scratch: shared memory that is idle by now (the operand ring), >= (1 + n_ranks) * NB3 * OUT_LIMBS3 words.
+__device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool has_work, uint32_t* s_E, bool* s_last, uint32_t* scratch) {
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (uint32_t i = tid; i < 2 * NB3 * 96; i += blockDim.x) s_E[i] = 0;
     __syncthreads();
@@ -241,13 +242,55 @@ __device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool
             limb |= (uint32_t)(acc & 0xffu) << (8 * (k & 3u));
             acc >>= 8;
             if ((k & 3u) == 3u) {
-                P.rp.host_out[tid * OUT_LIMBS3 + (k >> 2)] = limb;
+                scratch[tid * OUT_LIMBS3 + (k >> 2)] = limb;
                 limb = 0;
             }
         }
     }
-    __threadfence_system();
     __syncthreads();
+    if (tid >= 32) return;
+    constexpr uint32_t NW = NB3 * OUT_LIMBS3;
+    if (P.rp.peer_mail) {
+        // sharded polynomial: all-to-all of the six integers over NVLink peer memory — every limb ONE 8-byte {limb, sequence
+        // number} store into the receiver's mailbox (kernels.cuh mail_store: single-copy atomic), then the integer sums over
+        // the ranks (identical on every rank; they fit the limbs: 8 ranks add 3 bits to < 2^800)
+        const sck::RoundParams& p = P.rp;
+        const uint32_t lane = tid, G = p.n_ranks;
+        uint32_t* rows = scratch + NW;
+        for (uint32_t w = lane; w < NW; w += 32) {
+            const uint32_t v = scratch[w];
+            for (uint32_t g = 0; g < G; g++) sck::mail_store(p.peer_mail[g] + ((size_t)p.mail_slot * G + p.rank) * sck::MAIL_WORDS + 2 * w, v, p.mail_seq);
+        }
+        const uint32_t* mine = p.peer_mail[p.rank] + (size_t)p.mail_slot * G * sck::MAIL_WORDS;
+        for (uint32_t w = lane; w < NW; w += 32)
+            for (uint32_t g = 0; g < G; g++) {
+                uint32_t d, f;
+                const long long t0 = clock64();
+                for (;;) {
+                    sck::mail_load(mine + (size_t)g * sck::MAIL_WORDS + 2 * w, d, f);
+                    if (f == p.mail_seq) break;
+                    if (clock64() - t0 > p.mail_timeout) {  // a peer died: report instead of hanging the GPU
+                        *p.comm_error = 1;
+                        d = 0;
+                        break;
+                    }
+                }
+                rows[g * NW + w] = d;
+            }
+        __syncwarp();
+        if (lane < NB3) {
+            unsigned long long c = 0;
+            for (uint32_t i = 0; i < OUT_LIMBS3; i++) {
+                for (uint32_t g = 0; g < G; g++) c += rows[g * NW + lane * OUT_LIMBS3 + i];
+                scratch[lane * OUT_LIMBS3 + i] = (uint32_t)c;
+                c >>= 32;
+            }
+        }
+        __syncwarp();
+    }
+    for (uint32_t w = tid; w < NW; w += 32) P.rp.host_out[w] = scratch[w];
+    __threadfence_system();
+    __syncwarp();
     if (tid == 0 && P.rp.host_flag) *P.rp.host_flag = P.rp.seq;
 }
 
@@ -374,7 +417,7 @@ __global__ void __launch_bounds__(G * 128 + 64, 1) gemm_round1_kernel(const Para
     __syncwarp();
     tcf::tc_fence_before();
     __syncthreads();
-    epilogue3(P, tmem, items_of(0) > 0, s_E, &s_last);
+    epilogue3(P, tmem, items_of(0) > 0, s_E, &s_last, reinterpret_cast<uint32_t*>(smem));
     __syncthreads();
     if (warp == 0) tcf::tmem_dealloc(tmem, 128);
 }
@@ -625,7 +668,7 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
     __syncwarp();
     tcf::tc_fence_before();
     __syncthreads();
-    epilogue3(P, tmem, sp.n_items(0) > 0, s_E, &s_last);
+    epilogue3(P, tmem, sp.n_items(0) > 0, s_E, &s_last, reinterpret_cast<uint32_t*>(smem));
     __syncthreads();
     if (warp == 0) tcf::tmem_dealloc(tmem, 512);
 }

@@ -431,7 +431,10 @@ constexpr uint32_t GEMM_LIMBS3 = gsum::OUT_LIMBS3, GEMM_NB3 = gsum::NB3;
 
 // May this round (n_pairs output pairs; fold = rounds >= 2) run on the contraction kernels?
 bool gemm_round_ok(const sc_prover* p, unsigned long long n_pairs, bool fold) {
-    if (!p->gemm_shape || p->comm || p->is_shard || !p->host_post || !p->direct_results || p->n_products > gsum::MAX_PRODUCTS) return false;
+    if (!p->gemm_shape || !p->host_post || !p->direct_results || p->n_products > gsum::MAX_PRODUCTS) return false;
+    // a shard of a sharded polynomial: only when this round runs the fused peer-memory exchange (the last CTA then exchanges
+    // the six integers with the other ranks before it publishes)
+    if ((p->comm || p->is_shard) && !(p->comm && p->exchange)) return false;
     if (p->n_products > 1)
         for (uint32_t k = 0; k < p->n_products; k++)
             if (!p->h_scaled[k]) return false;  // a coefficient that is not inside a table would have to be applied per product

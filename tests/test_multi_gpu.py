@@ -67,6 +67,43 @@ def test_single_process_sharded_prover_matches_oracle(orc, world):
         del st
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_single_process_sharded_contraction_rounds(orc, monkeypatch, world):
+    """Degree-3 products on a sharded handle: the tensor-core contraction kernels (csrc/gemm_sum.cuh) run on every shard and their
+    last CTA exchanges the six big integers through the peer mailboxes.  Thresholds forced down so that round 1 AND fold rounds
+    take that path at test sizes; whole proofs and final tables against the UNSHARDED oracle, caller-driven rounds too."""
+    import sumcheck_b200 as sc
+    from helpers import limbs
+    monkeypatch.setenv("SC_TC_MIN_PAIRS", "128")
+    monkeypatch.setenv("SC_RES_MAX_PAIRS", "64")
+    monkeypatch.setenv("SC_REPL_LOG2", "8")   # stay sharded until the global tables are down to 2^8 elements
+    devs = _devices(world)
+    for nv, n_products, seed in [(12, 1, 41), (13, 3, 42)]:
+        tabs, prods = _instance(orc, nv, n_products, 3, seed)
+        poly = sc.ListOfProductsOfPolynomials.new(nv)
+        for c, ix in prods:
+            poly.add_product([tabs[j] for j in ix], c)
+        st = sc.IPForMLSumcheck.prover_init(poly, device=devs)
+        want, rand, fin = orc.ml_prove(orc.Poly(nv, tabs, prods))
+        for rep in range(2):
+            ev = np.zeros((nv, 4, 4), dtype=np.uint64)
+            st.prove_into(sc.Blake2b512Rng.setup(), ev)
+            assert np.array_equal(ev, want), f"world {world} nv {nv} rep {rep}"
+            assert st.gemm_round_count() >= 3
+            for j in range(len(tabs)):
+                assert np.array_equal(st.table(j), fin[j])
+            st.reset()
+        # caller-driven rounds (sc_prove_round): same kernels, the transcript on the caller's side
+        ost = orc.Prover(orc.Poly(nv, tabs, prods))
+        v = None
+        for i in range(5):
+            m = sc.IPForMLSumcheck.prove_round(st, v)
+            om = ost.prove_round(None if v is None else v.randomness)
+            assert np.array_equal(m.evaluations, om), f"round {i + 1}"
+            v = sc.VerifierMsg(limbs(1000 + i))
+        del st
+
+
 def test_single_process_interactive_rounds_and_tables(orc):
     """prove_round through the facade: every rank runs the round on its own thread; the folded tables (shards concatenated in
     rank order while sharded, the replicated copy afterwards) equal the oracle's after every round; edge challenges."""
