@@ -61,6 +61,11 @@ struct Params {
     long long* prof;              // SC_GEMM_PROF=1: [16] cycle counters summed over the CTAs (waits per role), else null
 };
 
+// phase markers (SC_GEMM_PROF): max over the CTAs of the cycles since the CTA started, slots 12..
+__device__ __forceinline__ void prof_mark(long long* prof, int slot, long long t_start) {
+    if (prof && threadIdx.x == 0) atomicMax((unsigned long long*)prof + slot, (unsigned long long)(clock64() - t_start));
+}
+
 struct ProfTimer {  // accumulates clock64 intervals of one thread; flushed with one atomicAdd per counter at the end
     long long acc = 0, t0 = 0;
     __device__ __forceinline__ void start(bool on) { if (on) t0 = clock64(); }
@@ -177,8 +182,10 @@ constexpr uint32_t NB3 = 6, DIAG3 = 95, OUT_LIMBS3 = 26;
 
 // s_E: [2][NB3 * 96] (low / high 16-bit halves of the accumulators, summed as u32).  Called by the whole CTA; warps 0..3 read TMEM.
 // scratch: shared memory that is idle by now (the operand ring), >= (1 + n_ranks) * NB3 * OUT_LIMBS3 words.
-__device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool has_work, uint32_t* s_E, bool* s_last, uint32_t* scratch) {
+__device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool has_work, uint32_t* s_E, bool* s_last, uint32_t* scratch,
+                                          long long t_start = 0) {
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    prof_mark(P.prof, 13, t_start);  // main loop done
     for (uint32_t i = tid; i < 2 * NB3 * 96; i += blockDim.x) s_E[i] = 0;
     __syncthreads();
     tcf::tc_fence_after();
@@ -211,6 +218,7 @@ __device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool
     }
     __threadfence();
     __syncthreads();
+    prof_mark(P.prof, 14, t_start);  // totals added
     if (tid == 0) {
         const unsigned int ticket = atomicAdd(P.rp.counter, 1u);
         *s_last = (ticket == gridDim.x - 1);
@@ -237,6 +245,7 @@ __device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool
     if (tid < NB3) {  // Z = sum_k 2^(8k) totals[k]: byte-serial carry into OUT_LIMBS3 limbs
         unsigned long long acc = 0;
         uint32_t limb = 0;
+#pragma unroll 8
         for (uint32_t k = 0; k < OUT_LIMBS3 * 4; k++) {
             if (k < DIAG3) acc += s_tot[tid * 96 + k];
             limb |= (uint32_t)(acc & 0xffu) << (8 * (k & 3u));
@@ -292,6 +301,7 @@ __device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool
     __threadfence_system();
     __syncwarp();
     if (tid == 0 && P.rp.host_flag) *P.rp.host_flag = P.rp.seq;
+    prof_mark(P.prof, 15, t_start);  // published (last CTA)
 }
 
 // ================================================================================================ round 1 (no fold), degree 3
@@ -479,6 +489,7 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
     __shared__ CsrCache s_csr;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const sck::RoundParams& p = P.rp;
+    const long long t_start = P.prof ? clock64() : 0;
     load_csr(s_csr, p, true);
     uint8_t* const bmat = smem + L::BMAT;
     if (tid == 0) {
@@ -498,20 +509,22 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
         tcf::fence_mbar_init();
     }
     if (warp == 0) tcf::tmem_alloc(&s_tmem, 512);
-    {
-        Fr r;
+    tcf::tc_fence_before();
+    __syncthreads();  // barriers, tensor memory and the product list are ready: the TMA warp starts staging tiles right away ...
+    tcf::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    if (warp < 2) {   // ... while warps 0 and 1 expand the challenge into the constants matrix, which only the first
+        Fr r;         // fix_variables MMA waits for (named barrier 1: these two warps arrive, the MMA-issuing warp syncs)
 #pragma unroll
         for (int i = 0; i < 8; i++) r.l[i] = p.r[i];
         tcf::build_bmat(r, bmat);
+        tcf::fence_proxy_async_smem();
+        asm volatile("bar.arrive 1, 96;" ::: "memory");
     }
-    tcf::fence_proxy_async_smem();
-    tcf::tc_fence_before();
-    __syncthreads();
-    tcf::tc_fence_after();
-    const uint32_t tmem = s_tmem;
     const Split<G> sp(P.items);
     const bool one_product = p.n_products == 1;
     const bool pf = P.prof != nullptr && lane == 0;
+    prof_mark(P.prof, 12, t_start);  // prologue done
     if (warp < G * 4) {
         // ---------------------------------------------------------------------------------------------------- compute group
         const uint32_t g = warp >> 2, t = tid & 127u;
@@ -604,6 +617,8 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
         }
     } else if (warp == W_FOLD) {
         // ---------------------------------------------------------------------------------------------------- fix_variables MMAs
+        asm volatile("bar.sync 1, 96;" ::: "memory");  // the constants matrix is in shared memory (written through the generic proxy, fenced)
+        tcf::tc_fence_after();
         if (lane == 0) {
             ProfTimer t_sf, t_ae, t_all, t_mma;
             t_all.start(pf);
@@ -668,7 +683,7 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
     __syncwarp();
     tcf::tc_fence_before();
     __syncthreads();
-    epilogue3(P, tmem, sp.n_items(0) > 0, s_E, &s_last, reinterpret_cast<uint32_t*>(smem));
+    epilogue3(P, tmem, sp.n_items(0) > 0, s_E, &s_last, reinterpret_cast<uint32_t*>(smem), t_start);
     __syncthreads();
     if (warp == 0) tcf::tmem_dealloc(tmem, 512);
 }

@@ -481,8 +481,8 @@ int launch_gemm_round(sc_prover* p, const sck::RoundParams& rp, bool fold, unsig
             cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
             cudaFree(d_prof);
             const double ctas = (double)((G.items + 2) / 3 < (uint32_t)sms ? (G.items + 2) / 3 : (uint32_t)sms), cw = ctas * 12;
-            fprintf(stderr, "gemm %s items %u: per compute warp: total %.0f, wait acc_full %.0f, wait x_empty %.0f | fold warp per CTA: total %.0f, wait slot_full %.0f, acc_empty %.0f, mma issue + commit %.0f | TMA warp: total %.0f, wait slot_empty %.0f | sum warp: wait x_full %.0f, issue %.0f\n",
-                    fold ? "fold" : "round1", G.items, h[2] / cw, h[0] / cw, h[1] / cw, h[6] / ctas, h[3] / ctas, h[4] / ctas, h[8] / ctas, h[11] / ctas, h[5] / ctas, h[7] / ctas, h[10] / ctas);
+            fprintf(stderr, "gemm %s items %u: per compute warp: total %.0f, wait acc_full %.0f, wait x_empty %.0f | fold warp per CTA: total %.0f, wait slot_full %.0f, acc_empty %.0f, mma issue + commit %.0f | TMA warp: total %.0f, wait slot_empty %.0f | sum warp: wait x_full %.0f, issue %.0f | cycles since CTA start (max): prologue %lld, loop %lld, totals %lld, published %lld\n",
+                    fold ? "fold" : "round1", G.items, h[2] / cw, h[0] / cw, h[1] / cw, h[6] / ctas, h[3] / ctas, h[4] / ctas, h[8] / ctas, h[11] / ctas, h[5] / ctas, h[7] / ctas, h[10] / ctas, h[12], h[13], h[14], h[15]);
         }
     }
     return SC_OK;
