@@ -14,12 +14,12 @@ cudaError_t init_constants() { return fr::fr_init_constants(); }  // this TU's c
 #define SC_GEMM_G1 3  // compute groups per CTA, round 1 (three: 144 registers per thread leave room for the next item's pairs)
 #endif
 #ifndef SC_GEMM_GF
-#define SC_GEMM_GF 3  // compute groups per CTA, fold rounds (shared memory and tensor memory allow three)
+#define SC_GEMM_GF 3  // compute groups per CTA, fold rounds of three-table products (shared memory and tensor memory allow three)
 #endif
-constexpr int G1 = SC_GEMM_G1, GF = SC_GEMM_GF;
-
-int groups_round1() { return G1; }
-int groups_fold() { return GF; }
+#ifndef SC_GEMM_GF4
+#define SC_GEMM_GF4 2  // ... of four-table products: the 192 x 192 contraction takes 384 of the 512 tensor-memory columns
+#endif
+constexpr int G1 = SC_GEMM_G1, GF = SC_GEMM_GF, GF4 = SC_GEMM_GF4;
 
 // TAG: one instantiation (and one set of per-device flags) per kernel — the kernels share a function-pointer type
 template <int TAG, class K>
@@ -36,7 +36,7 @@ static cudaError_t prepare(K kernel, size_t smem) {
     if (getenv("SC_DEBUG")) {
         cudaFuncAttributes fa;
         if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess)
-            fprintf(stderr, "gemm kernel: %d registers, %zu B static + %zu B dynamic shared memory\n", fa.numRegs, fa.sharedSizeBytes, smem);
+            fprintf(stderr, "gemm kernel %d: %d registers, %zu B static + %zu B dynamic shared memory\n", TAG, fa.numRegs, fa.sharedSizeBytes, smem);
     }
     ready_dev[dev] = true;
     return cudaSuccess;
@@ -49,23 +49,31 @@ static int grid_for(uint32_t items, int G, int sms) {
 }
 
 // items a single launch may carry (every CTA at most MAX_ITEMS_PER_CTA per group)
-unsigned long long max_items_round1(int sms) { return (unsigned long long)sms * G1 * MAX_ITEMS_PER_CTA; }
-unsigned long long max_items_fold(int sms) { return (unsigned long long)sms * GF * MAX_ITEMS_PER_CTA; }
+unsigned long long max_items_round1(int sms, int mm) { (void)mm; return (unsigned long long)sms * G1 * MAX_ITEMS_PER_CTA; }
+unsigned long long max_items_fold(int sms, int mm) { return (unsigned long long)sms * (mm == 4 ? GF4 : GF) * MAX_ITEMS_PER_CTA; }
 
-cudaError_t launch_round1(const Params& P, int sms, cudaStream_t stream) {
-    const size_t smem = R1Smem<G1>::BYTES;
-    cudaError_t e = prepare<1>(gemm_round1_kernel<G1>, smem);
+template <int TAG, int G, int MM>
+static cudaError_t launch_r1(const Params& P, int sms, cudaStream_t stream) {
+    const size_t smem = R1Smem<G, MM>::BYTES;
+    cudaError_t e = prepare<TAG>(gemm_round1_kernel<G, MM>, smem);
     if (e != cudaSuccess) return e;
-    gemm_round1_kernel<G1><<<grid_for(P.items, G1, sms), G1 * 128 + 64, smem, stream>>>(P);
+    gemm_round1_kernel<G, MM><<<grid_for(P.items, G, sms), G * 128 + 64, smem, stream>>>(P);
+    return cudaGetLastError();
+}
+template <int TAG, int G, int MM>
+static cudaError_t launch_f(const Params& P, int sms, cudaStream_t stream) {
+    const size_t smem = FoldSmem<G, MM>::BYTES;
+    cudaError_t e = prepare<TAG>(gemm_fold_kernel<G, MM>, smem);
+    if (e != cudaSuccess) return e;
+    gemm_fold_kernel<G, MM><<<grid_for(P.items, G, sms), G * 128 + 96, smem, stream>>>(P);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fold(const Params& P, int sms, cudaStream_t stream) {
-    const size_t smem = FoldSmem<GF>::BYTES;
-    cudaError_t e = prepare<2>(gemm_fold_kernel<GF>, smem);
-    if (e != cudaSuccess) return e;
-    gemm_fold_kernel<GF><<<grid_for(P.items, GF, sms), GF * 128 + 96, smem, stream>>>(P);
-    return cudaGetLastError();
+cudaError_t launch_round1(const Params& P, int mm, int sms, cudaStream_t stream) {
+    return mm == 4 ? launch_r1<3, G1, 4>(P, sms, stream) : launch_r1<1, G1, 3>(P, sms, stream);
+}
+cudaError_t launch_fold(const Params& P, int mm, int sms, cudaStream_t stream) {
+    return mm == 4 ? launch_f<4, GF4, 4>(P, sms, stream) : launch_f<2, GF, 3>(P, sms, stream);
 }
 
 }  // namespace gsum

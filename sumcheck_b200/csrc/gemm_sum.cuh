@@ -32,19 +32,20 @@ constexpr uint32_t TILE = 128;               // pairs per work item = threads pe
 constexpr uint32_t OUT_SLOT_WORDS = 512;     // mapped result slot: NB * OUT_LIMBS words, sequence flag in the last word
 constexpr uint32_t MAX_ITEMS_PER_CTA = 256;  // 4 K-steps of 32 pairs each: every s32 accumulator stays below 2^31
 constexpr uint32_t TOT_STRIDE = 128;         // u64 totals per block pair (>= number of anti-diagonals)
-constexpr uint32_t MAX_PRODUCTS = 32;        // the CSR of the product list is cached in shared memory (3 entries per product)
+constexpr uint32_t MAX_PRODUCTS = 32;        // the CSR of the product list is cached in shared memory (3 or 4 entries per product)
 
 // The product list as the kernels use it, in shared memory: a dependent chain of global loads (offsets -> indices -> table
 // pointer) per work item costs the single producer thread ~1700 cycles per table tile (measured) and made it the bottleneck.
 struct CsrCache {
-    uint32_t idx[3 * MAX_PRODUCTS];          // table index of CSR entry 3k + j
-    uint32_t first[3 * MAX_PRODUCTS];        // 1 where the entry is the first use of its table (that use stores the fold)
-    const uint32_t* in[3 * MAX_PRODUCTS];    // tab_in of the entry
-    uint32_t* out[3 * MAX_PRODUCTS];         // tab_out of the entry (fold rounds)
+    uint32_t idx[4 * MAX_PRODUCTS];          // table index of CSR entry MM k + j
+    uint32_t first[4 * MAX_PRODUCTS];        // 1 where the entry is the first use of its table (that use stores the fold)
+    const uint32_t* in[4 * MAX_PRODUCTS];    // tab_in of the entry
+    uint32_t* out[4 * MAX_PRODUCTS];         // tab_out of the entry (fold rounds)
 };
+template <int MM>
 __device__ __forceinline__ void load_csr(CsrCache& c, const sck::RoundParams& p, bool fold) {
-    for (uint32_t e = threadIdx.x; e < 3 * p.n_products; e += blockDim.x) {
-        const uint32_t jj = p.prod_offsets[e / 3] + e % 3, idx = p.prod_indices[jj];
+    for (uint32_t e = threadIdx.x; e < MM * p.n_products; e += blockDim.x) {
+        const uint32_t jj = p.prod_offsets[e / MM] + e % MM, idx = p.prod_indices[jj];
         c.idx[e] = idx;
         c.first[e] = p.prod_first[jj];
         c.in[e] = p.tab_in[idx];
@@ -76,10 +77,29 @@ struct ProfTimer {  // accumulates clock64 intervals of one thread; flushed with
 // ---- MN-major operand descriptors (checked by tools/microbench/gemmsum.cu) ------------------------------------------------------
 // [k = pair][bytes] with the bytes of a pair contiguous: 128-byte rows + SWIZZLE_128B (layout type 2, 8-row groups 1024 B apart)
 // or 64-byte rows + SWIZZLE_64B (layout type 4, 8-row groups 512 B apart).  K = 32 pairs per instruction.
-__device__ __forceinline__ uint64_t mn_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
-    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
+// lbo_bytes: distance between swizzle atoms along the byte (MN) direction, for operands wider than one atom.
+__device__ __forceinline__ uint64_t mn_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type, uint32_t lbo_bytes = 16) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)layout_type << 61);
 }
+
+// ---- the two shapes --------------------------------------------------------------------------------------------------------------
+// MM = multiplicands per product.  The X side is always the first TWO tables of a product: three plain products q0, q1, qs of 64 bytes
+// (X = 192 bytes per pair: XA = [q0 | q1] with SWIZZLE_128B, XQ = qs with SWIZZLE_64B).  The Y side is
+//   MM = 3: the third table's pair [a2 | b2], two blocks of 32 bytes (one SWIZZLE_64B array, N = 64);
+//   MM = 4: the three plain products s0, s1, ss of tables 2 and 3, three blocks of 64 bytes (three SWIZZLE_64B arrays 8 KiB apart,
+//           N = 192 through the descriptor's leading byte offset) — again no modular arithmetic anywhere in the hot loop.
+// D = X^T Y has 3 x NBY block pairs; block pair (i, j) yields sum_b X_i * Y_j as an integer of OUT_LIMBS limbs.
+template <int MM>
+struct Shape;
+template <>
+struct Shape<3> {
+    static constexpr uint32_t NBY = 2, BY = 32, N = 64, NB = 6, DIAG = 95, ES = 96, OUT_LIMBS = 26, Y_BYTES = 8192;
+};
+template <>
+struct Shape<4> {
+    static constexpr uint32_t NBY = 3, BY = 64, N = 192, NB = 9, DIAG = 127, ES = 128, OUT_LIMBS = 34, Y_BYTES = 24576;
+};
 // c_format S32 @4, a/b U8, a_major = b_major = MN @15/@16, N>>3 @17, M>>4 @24
 __host__ __device__ constexpr uint32_t idesc_u8_mn(uint32_t M, uint32_t N) {
     return (2u << 4) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -164,43 +184,59 @@ __device__ __forceinline__ void products_to_smem(const Fr& a0, const Fr& b0, con
     sts_sw64(XQ, row, o);
 }
 
-// ---- contraction of one 128-pair tile: D1 (128 x 64) += XA^T Y, D2 (64 x 64) += XQ^T Y; issued by ONE thread ----------------------
+// The three products of the Y side (MM = 4) into the group's three Y arrays
+__device__ __forceinline__ void y_products_to_smem(const Fr& a2, const Fr& b2, const Fr& a3, const Fr& b3, uint8_t* Y, uint32_t row) {
+    uint32_t o[16];
+    mul_plain(a2, a3, o);
+    sts_sw64(Y, row, o);
+    mul_plain(b2, b3, o);
+    sts_sw64(Y + 8192, row, o);
+    mul_plain(add_plain(a2, b2), add_plain(a3, b3), o);
+    sts_sw64(Y + 16384, row, o);
+}
+
+// ---- contraction of one 128-pair tile: D1 (128 x N) += XA^T Y, D2 (64 x N) += XQ^T Y; issued by ONE thread -----------------------
+template <int MM>
 __device__ __forceinline__ void issue_contraction(uint32_t xa_smem, uint32_t xq_smem, uint32_t y_smem, uint32_t tmem_d, uint32_t accumulate) {
-    constexpr uint32_t I128 = idesc_u8_mn(128, 64), I64 = idesc_u8_mn(64, 64);
+    constexpr uint32_t N = Shape<MM>::N, I128 = idesc_u8_mn(128, N), I64 = idesc_u8_mn(64, N);
 #pragma unroll
     for (uint32_t ks = 0; ks < 4; ks++) {
-        const uint64_t b = mn_desc(y_smem + ks * 2048u, 512, 4);
+        const uint64_t b = mn_desc(y_smem + ks * 2048u, 512, 4, 8192);
         umma(tmem_d, mn_desc(xa_smem + ks * 4096u, 1024, 2), b, I128, accumulate | ks);
-        umma(tmem_d + 64, mn_desc(xq_smem + ks * 2048u, 512, 4), b, I64, accumulate | ks);
+        umma(tmem_d + N, mn_desc(xq_smem + ks * 2048u, 512, 4), b, I64, accumulate | ks);
     }
 }
 
-// ---- epilogue: D -> anti-diagonal sums -> global totals -> (last CTA) the six integers --------------------------------------------
-// Degree-3 layout: D1 lanes 0..127 = byte u of q0 (lanes 0..63) / q1 (64..127), D2 rows 0..63 = byte u of qs in lanes
-// (u % 16) + 32 (u / 16); columns 0..31 = byte v of y0 = a2, 32..63 = byte v of y1 = b2.  Block pair bp = 2 i + j, diagonal k = u + v.
-constexpr uint32_t NB3 = 6, DIAG3 = 95, OUT_LIMBS3 = 26;
+// ---- epilogue: D -> anti-diagonal sums -> global totals -> (last CTA) the NB integers --------------------------------------------
+// D1 lanes 0..127 = byte u of q0 (lanes 0..63) / q1 (64..127), columns 0..N-1; D2 rows 0..63 = byte u of qs in lanes
+// (u % 16) + 32 (u / 16), columns N..2N-1; column c = byte c % BY of Y block c / BY.  Block pair bp = NBY i + j, diagonal k = u + v.
+constexpr uint32_t NB3 = Shape<3>::NB, OUT_LIMBS3 = Shape<3>::OUT_LIMBS;
 
-// s_E: [2][NB3 * 96] (low / high 16-bit halves of the accumulators, summed as u32).  Called by the whole CTA; warps 0..3 read TMEM.
-// scratch: shared memory that is idle by now (the operand ring), >= (1 + n_ranks) * NB3 * OUT_LIMBS3 words.
-__device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool has_work, uint32_t* s_E, bool* s_last, uint32_t* scratch,
-                                          long long t_start = 0) {
+// s_E: [2][NB * ES] (low / high 16-bit halves of the accumulators, summed as u32).  Called by the whole CTA; warps 0..3 read TMEM.
+// scratch: shared memory that is idle by now (the operand ring), >= (1 + n_ranks) * NB * OUT_LIMBS words.
+template <int MM>
+__device__ __forceinline__ void epilogue(const Params& P, uint32_t tmem_d, bool has_work, uint32_t* s_E, bool* s_last, uint32_t* scratch,
+                                         long long t_start = 0) {
+    using S_ = Shape<MM>;
+    constexpr uint32_t NB = S_::NB, ES = S_::ES, DIAG = S_::DIAG, OUT_LIMBS = S_::OUT_LIMBS, N = S_::N, BY = S_::BY, NBY = S_::NBY;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     prof_mark(P.prof, 13, t_start);  // main loop done
-    for (uint32_t i = tid; i < 2 * NB3 * 96; i += blockDim.x) s_E[i] = 0;
+    for (uint32_t i = tid; i < 2 * NB * ES; i += blockDim.x) s_E[i] = 0;
     __syncthreads();
     tcf::tc_fence_after();
     if (warp < 4 && has_work) {  // (a CTA without work never wrote its accumulators)
         const uint32_t lane_addr = tmem_d + ((warp * 32u) << 16);
         uint32_t S[32];
 #pragma unroll 1
-        for (uint32_t part = 0; part < 4; part++) {  // D1 columns 0..31, 32..63, D2 columns 0..31, 32..63
-            const bool second = part >= 2;
+        for (uint32_t part = 0; part < 2 * N / 32; part++) {  // 32 columns at a time: D1 first, then D2
+            const bool second = part >= N / 32;
             tcf::tmem_ld32(lane_addr + part * 32u, S);  // (whole warp: .sync.aligned)
             tcf::tmem_ld_wait();
             if (second && lane >= 16) continue;  // D2 (M = 64) lives in lanes 0..15 of every 32-lane quadrant
-            const uint32_t i = second ? 2u : (tid >> 6), u = second ? (warp * 16u + lane) : (tid & 63u), j = part & 1u;
-            uint32_t* lo = s_E + (2 * i + j) * 96 + u;
-            uint32_t* hi = lo + NB3 * 96;
+            const uint32_t i = second ? 2u : (tid >> 6), u = second ? (warp * 16u + lane) : (tid & 63u);
+            const uint32_t c0 = (second ? part - N / 32 : part) * 32u, j = c0 / BY, v0 = c0 % BY;
+            uint32_t* lo = s_E + (NBY * i + j) * ES + u + v0;
+            uint32_t* hi = lo + NB * ES;
 #pragma unroll
             for (int v = 0; v < 32; v++) {
                 atomicAdd(lo + v, S[v] & 0xffffu);
@@ -210,10 +246,10 @@ __device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool
     }
     tcf::tc_fence_before();
     __syncthreads();
-    for (uint32_t i = tid; i < NB3 * 96; i += blockDim.x) {
-        const uint32_t bp = i / 96, k = i % 96;
-        if (k >= DIAG3) continue;
-        const unsigned long long v = (unsigned long long)s_E[i] + ((unsigned long long)s_E[NB3 * 96 + i] << 16);
+    for (uint32_t i = tid; i < NB * ES; i += blockDim.x) {
+        const uint32_t bp = i / ES, k = i % ES;
+        if (k >= DIAG) continue;
+        const unsigned long long v = (unsigned long long)s_E[i] + ((unsigned long long)s_E[NB * ES + i] << 16);
         if (v) atomicAdd(P.totals + bp * TOT_STRIDE + k, v);
     }
     __threadfence();
@@ -228,43 +264,43 @@ __device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool
     __threadfence();
     if (tid == 0) *P.rp.counter = 0;
     if (!P.publish) return;
-    // the grid's totals into shared memory with independent loads (a dependent chain of 95 L2 round trips per integer cost
+    // the grid's totals into shared memory with independent loads (a dependent chain of L2 round trips per integer cost
     // ~25 us per launch), leaving the global copy zero for the next launch
-    unsigned long long* s_tot = reinterpret_cast<unsigned long long*>(s_E);  // [NB3][96]
+    unsigned long long* s_tot = reinterpret_cast<unsigned long long*>(s_E);  // [NB][ES]
     __syncthreads();
-    for (uint32_t i = tid; i < NB3 * 96; i += blockDim.x) {
-        const uint32_t bp = i / 96, k = i % 96;
+    for (uint32_t i = tid; i < NB * ES; i += blockDim.x) {
+        const uint32_t bp = i / ES, k = i % ES;
         unsigned long long v = 0;
-        if (k < DIAG3) {
+        if (k < DIAG) {
             v = __ldcg(P.totals + bp * TOT_STRIDE + k);
             P.totals[bp * TOT_STRIDE + k] = 0;
         }
         s_tot[i] = v;
     }
     __syncthreads();
-    if (tid < NB3) {  // Z = sum_k 2^(8k) totals[k]: byte-serial carry into OUT_LIMBS3 limbs
+    if (tid < NB) {  // Z = sum_k 2^(8k) totals[k]: byte-serial carry into OUT_LIMBS limbs
         unsigned long long acc = 0;
         uint32_t limb = 0;
 #pragma unroll 8
-        for (uint32_t k = 0; k < OUT_LIMBS3 * 4; k++) {
-            if (k < DIAG3) acc += s_tot[tid * 96 + k];
+        for (uint32_t k = 0; k < OUT_LIMBS * 4; k++) {
+            if (k < DIAG) acc += s_tot[tid * ES + k];
             limb |= (uint32_t)(acc & 0xffu) << (8 * (k & 3u));
             acc >>= 8;
             if ((k & 3u) == 3u) {
-                scratch[tid * OUT_LIMBS3 + (k >> 2)] = limb;
+                scratch[tid * OUT_LIMBS + (k >> 2)] = limb;
                 limb = 0;
             }
         }
     }
     __syncthreads();
     if (tid >= 32) return;
-    constexpr uint32_t NW = NB3 * OUT_LIMBS3;
+    constexpr uint32_t NW = NB * OUT_LIMBS;
     if (P.rp.peer_mail) {
-        // sharded polynomial: all-to-all of the six integers over NVLink peer memory — every limb ONE 8-byte {limb, sequence
+        // sharded polynomial: all-to-all of the integers over NVLink peer memory — every limb ONE 8-byte {limb, sequence
         // number} store into the receiver's mailbox (kernels.cuh mail_store: single-copy atomic), then the integer sums over
-        // the ranks (identical on every rank; they fit the limbs: 8 ranks add 3 bits to < 2^800)
+        // the ranks (identical on every rank; they fit the limbs: 8 ranks add 3 bits)
         const sck::RoundParams& p = P.rp;
-        const uint32_t lane = tid, G = p.n_ranks;
+        const uint32_t G = p.n_ranks;
         uint32_t* rows = scratch + NW;
         for (uint32_t w = lane; w < NW; w += 32) {
             const uint32_t v = scratch[w];
@@ -287,11 +323,11 @@ __device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool
                 rows[g * NW + w] = d;
             }
         __syncwarp();
-        if (lane < NB3) {
+        if (lane < NB) {
             unsigned long long c = 0;
-            for (uint32_t i = 0; i < OUT_LIMBS3; i++) {
-                for (uint32_t g = 0; g < G; g++) c += rows[g * NW + lane * OUT_LIMBS3 + i];
-                scratch[lane * OUT_LIMBS3 + i] = (uint32_t)c;
+            for (uint32_t i = 0; i < OUT_LIMBS; i++) {
+                for (uint32_t g = 0; g < G; g++) c += rows[g * NW + lane * OUT_LIMBS + i];
+                scratch[lane * OUT_LIMBS + i] = (uint32_t)c;
                 c >>= 32;
             }
         }
@@ -304,156 +340,10 @@ __device__ __forceinline__ void epilogue3(const Params& P, uint32_t tmem_d, bool
     prof_mark(P.prof, 15, t_start);  // published (last CTA)
 }
 
-// ================================================================================================ round 1 (no fold), degree 3
-// Tables 0 and 1 of the product are read by the threads (two LDG.256 per table), table 2 goes HBM -> shared memory by TMA with
-// 64-byte rows and is the Y operand as it lands.
-template <int G>
-struct R1Smem {
-    static constexpr uint32_t XA = 0, XQ = 16384, Y0 = 24576, Y1 = 32768, GROUP = 40960;
-    static constexpr size_t BYTES = (size_t)G * GROUP;
-};
-
-template <int G>
-__global__ void __launch_bounds__(G * 128 + 64, 1) gemm_round1_kernel(const Params P) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t y_full[G][2], y_empty[G][2], x_full[G], x_empty[G];
-    __shared__ uint32_t s_tmem;
-    __shared__ __align__(8) uint32_t s_E[2 * NB3 * 96];
-    __shared__ bool s_last;
-    __shared__ CsrCache s_csr;
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const sck::RoundParams& p = P.rp;
-    load_csr(s_csr, p, false);
-    if (tid == 0) {
-        if (tcf::smem_u32(smem) & 1023u) __trap();
-        for (int g = 0; g < G; g++) {
-            tcf::mbar_init(&y_full[g][0], 1);
-            tcf::mbar_init(&y_full[g][1], 1);
-            tcf::mbar_init(&y_empty[g][0], 1);
-            tcf::mbar_init(&y_empty[g][1], 1);
-            tcf::mbar_init(&x_full[g], 4);
-            tcf::mbar_init(&x_empty[g], 1);
-        }
-        tcf::fence_mbar_init();
-    }
-    if (warp == 0) tcf::tmem_alloc(&s_tmem, 128);
-    tcf::tc_fence_before();
-    __syncthreads();
-    tcf::tc_fence_after();
-    const uint32_t tmem = s_tmem;
-    const uint32_t stride = gridDim.x * G;
-    // items of group g: w = blockIdx.x * G + g + n * stride < P.items
-    auto items_of = [&](uint32_t g) {
-        const uint32_t first = blockIdx.x * G + g;
-        return first < P.items ? (P.items - first + stride - 1) / stride : 0u;
-    };
-    if (warp < G * 4) {
-        // ---------------------------------------------------------------------------------------------------- compute group
-        const uint32_t g = warp >> 2, t = tid & 127u;
-        uint8_t* const base = smem + (size_t)g * R1Smem<G>::GROUP;
-        const uint32_t n_items = items_of(g);
-        const bool one_product = p.n_products == 1;
-        Fr a0, b0, a1, b1, na0, nb0, na1, nb1;
-        // this thread's pairs of the product's first two tables for item n (the next item's are requested before this item's
-        // products are computed: a group always has 16 KiB of loads in flight)
-        auto fetch = [&](uint32_t n, Fr& x0, Fr& y0, Fr& x1, Fr& y1) {
-            const uint32_t w = blockIdx.x * G + g + n * stride;
-            const uint32_t k = one_product ? 0u : w % p.n_products, tile = p.tile_base + (one_product ? w : w / p.n_products);
-            const unsigned long long b = (unsigned long long)tile * TILE + t;
-            const uint32_t* s0 = s_csr.in[3 * k] + b * 16;
-            const uint32_t* s1 = s_csr.in[3 * k + 1] + b * 16;
-            x0 = fr::load_stream(s0);
-            y0 = fr::load_stream(s0 + 8);
-            x1 = fr::load_stream(s1);
-            y1 = fr::load_stream(s1 + 8);
-        };
-        if (n_items) fetch(0, a0, b0, a1, b1);
-        for (uint32_t n = 0; n < n_items; n++) {
-            if (n + 1 < n_items) fetch(n + 1, na0, nb0, na1, nb1);
-            if (n > 0) tcf::mbar_wait(&x_empty[g], (n - 1) & 1u);  // the contraction of item n-1 has read the X operand
-            products_to_smem(a0, b0, a1, b1, base + R1Smem<G>::XA, base + R1Smem<G>::XQ, t);
-            a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
-            tcf::fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) tcf::mbar_arrive(&x_full[g]);
-        }
-    } else if (warp == G * 4) {
-        // ---------------------------------------------------------------------------------------------------- P0: TMA of the Y tiles
-        if (lane == 0) {
-            uint32_t n_items[G], max_items = 0;
-            for (int g = 0; g < G; g++) {
-                n_items[g] = items_of(g);
-                max_items = n_items[g] > max_items ? n_items[g] : max_items;
-            }
-            for (uint32_t n = 0; n < max_items; n++)
-                for (int g = 0; g < G; g++) {
-                    if (n >= n_items[g]) continue;
-                    const uint32_t s = n & 1u;
-                    if (n >= 2) tcf::mbar_wait(&y_empty[g][s], ((n >> 1) - 1u) & 1u);
-                    const uint32_t w = blockIdx.x * G + g + n * stride;
-                    const uint32_t k = w % p.n_products, tile = p.tile_base + w / p.n_products;
-                    const uint32_t idx = s_csr.idx[3 * k + 2];
-                    tcf::mbar_expect_tx(&y_full[g][s], 8192);
-                    tcf::tma_load_tile(smem + (size_t)g * R1Smem<G>::GROUP + (s ? R1Smem<G>::Y1 : R1Smem<G>::Y0), (const uint8_t*)P.ymaps + (size_t)idx * 128,
-                                       &y_full[g][s], tile * TILE);
-                }
-        }
-    } else {
-        // ---------------------------------------------------------------------------------------------------- P1: contraction MMAs
-        if (lane == 0) {
-            uint32_t n_items[G], max_items = 0;
-            for (int g = 0; g < G; g++) {
-                n_items[g] = items_of(g);
-                max_items = n_items[g] > max_items ? n_items[g] : max_items;
-            }
-            uint32_t acc = 0;
-            for (uint32_t n = 0; n < max_items; n++)
-                for (int g = 0; g < G; g++) {
-                    if (n >= n_items[g]) continue;
-                    const uint32_t s = n & 1u, gb = tcf::smem_u32(smem + (size_t)g * R1Smem<G>::GROUP);
-                    tcf::mbar_wait(&y_full[g][s], (n >> 1) & 1u);
-                    tcf::mbar_wait(&x_full[g], n & 1u);
-                    tcf::tc_fence_after();
-                    issue_contraction(gb + R1Smem<G>::XA, gb + R1Smem<G>::XQ, gb + (s ? R1Smem<G>::Y1 : R1Smem<G>::Y0), tmem, acc);
-                    acc = 1;
-                    tcf::umma_commit(&x_empty[g]);
-                    tcf::umma_commit(&y_empty[g][s]);
-                }
-            // every MMA has completed once the last commit of every group has arrived
-            for (int g = 0; g < G; g++)
-                if (n_items[g]) tcf::mbar_wait(&x_empty[g], (n_items[g] - 1) & 1u);
-        }
-    }
-    __syncwarp();
-    tcf::tc_fence_before();
-    __syncthreads();
-    epilogue3(P, tmem, items_of(0) > 0, s_E, &s_last, reinterpret_cast<uint32_t*>(smem));
-    __syncthreads();
-    if (warp == 0) tcf::tmem_dealloc(tmem, 128);
-}
-
-// ================================================================================================ fold rounds, degree 3
-// Every table tile (128 rows x 128 bytes = old[4b..4b+3]) goes HBM -> shared memory by TMA into a ring shared by the groups
-// (warp W_TMA); warp W_FOLD issues the fix_variables MMAs (tc_fold.cuh) into the owning group's accumulator (two per group,
-// alternating); the group's thread t reads out new[2b], new[2b+1] of pair b = tile * 128 + t, stores them (the folded table)
-// and, once it holds the pairs of the product's first two tables, writes the three plain products; the folded pair of the
-// third table is the Y operand; warp W_SUM issues the contraction MMAs.  Each producer warp walks the same sequence of units
-// (item n, multiplicand j, group g) — g innermost, so consecutive units belong to different groups — and never computes
-// anything but a ring slot and a barrier phase (a producer that also chased the product list through global memory cost
-// ~1700 cycles per unit and starved every group: measured).
-template <int G>
-struct FoldSmem {
-    static constexpr uint32_t RING_SLOTS = 6;
-    static constexpr uint32_t GROUPS = RING_SLOTS * tcf::TILE_BYTES;
-    static constexpr uint32_t XA = 0, XQ = 16384, Y = 24576, GROUP = 32768;
-    static constexpr uint32_t BMAT = GROUPS + G * GROUP;
-    static constexpr size_t BYTES = (size_t)BMAT + tcf::BMAT_BYTES;
-};
-
 // Work split of one CTA: group g owns the items w = blockIdx.x * G + g + n * stride, n < n_items(g).  n_items is non-increasing
 // in g and differs by at most one between groups, so all G groups take part in every step n < n_min and the first `rem` groups
-// in the (possibly) partial last step n = n_min.  Unit (n, j, g) is the u-th of the CTA with u = 3 G n + j * groups(n) + g.
-template <int G>
+// in the (possibly) partial last step n = n_min.  Unit (n, j, g) is the u-th of the CTA with u = MM G n + j * groups(n) + g (MM table tiles per item).
+template <int G, int MM = 3>
 struct Split {
     uint32_t n_min, rem, stride, first;
     __device__ __forceinline__ Split(uint32_t items) {
@@ -472,25 +362,183 @@ struct Split {
     __device__ __forceinline__ uint32_t n_items(uint32_t g) const { return n_min + (g < rem ? 1u : 0u); }
     __device__ __forceinline__ uint32_t steps() const { return n_min + (rem ? 1u : 0u); }
     __device__ __forceinline__ uint32_t groups(uint32_t n) const { return n < n_min ? (uint32_t)G : rem; }
-    __device__ __forceinline__ uint32_t unit(uint32_t n, uint32_t j, uint32_t g) const { return 3u * G * n + j * groups(n) + g; }
+    __device__ __forceinline__ uint32_t unit(uint32_t n, uint32_t j, uint32_t g) const { return (uint32_t)MM * G * n + j * groups(n) + g; }
     __device__ __forceinline__ uint32_t item(uint32_t n, uint32_t g) const { return first + g + n * stride; }
 };
 
-template <int G>
+// ================================================================================================ round 1 (no fold)
+// MM = 3: tables 0 and 1 of the product are read by the threads (two LDG.256 per table, one item ahead), table 2 goes HBM -> shared
+// memory by TMA with 64-byte rows and is the Y operand as it lands.  MM = 4: all four tables are read by the threads (both
+// operands are products).
+template <int G, int MM>
+struct R1Smem {
+    static constexpr uint32_t XA = 0, XQ = 16384, Y0 = 24576, Y1 = Y0 + Shape<MM>::Y_BYTES;  // MM = 3: two Y slots (TMA, double-buffered)
+    static constexpr uint32_t GROUP = MM == 3 ? Y1 + 8192 : Y1;
+    static constexpr size_t BYTES = (size_t)G * GROUP;
+};
+
+template <int G, int MM>
+__global__ void __launch_bounds__(G * 128 + 64, 1) gemm_round1_kernel(const Params P) {
+    using L = R1Smem<G, MM>;
+    using S_ = Shape<MM>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t y_full[G][2], y_empty[G][2], x_full[G], x_empty[G];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint32_t s_E[2 * S_::NB * S_::ES];
+    __shared__ bool s_last;
+    __shared__ CsrCache s_csr;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const sck::RoundParams& p = P.rp;
+    load_csr<MM>(s_csr, p, false);
+    if (tid == 0) {
+        if (tcf::smem_u32(smem) & 1023u) __trap();
+        for (int g = 0; g < G; g++) {
+            tcf::mbar_init(&y_full[g][0], 1);
+            tcf::mbar_init(&y_full[g][1], 1);
+            tcf::mbar_init(&y_empty[g][0], 1);
+            tcf::mbar_init(&y_empty[g][1], 1);
+            tcf::mbar_init(&x_full[g], 4);
+            tcf::mbar_init(&x_empty[g], 1);
+        }
+        tcf::fence_mbar_init();
+    }
+    constexpr uint32_t TMEM_COLS = MM == 3 ? 128 : 512;  // 2 N accumulator columns, a power of two
+    if (warp == 0) tcf::tmem_alloc(&s_tmem, TMEM_COLS);
+    tcf::tc_fence_before();
+    __syncthreads();
+    tcf::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const Split<G> sp(P.items);
+    const bool one_product = p.n_products == 1;
+    auto locate = [&](uint32_t n, uint32_t g, uint32_t& k, uint32_t& tile) {
+        const uint32_t w = sp.item(n, g);
+        k = one_product ? 0u : w % p.n_products;
+        tile = p.tile_base + (one_product ? w : w / p.n_products);
+    };
+    if (warp < G * 4) {
+        // ---------------------------------------------------------------------------------------------------- compute group
+        const uint32_t g = warp >> 2, t = tid & 127u;
+        uint8_t* const base = smem + (size_t)g * L::GROUP;
+        const uint32_t n_items = sp.n_items(g);
+        // this thread's pairs of two tables of the product for item n
+        auto fetch = [&](uint32_t n, uint32_t j, Fr& x0, Fr& y0, Fr& x1, Fr& y1) {
+            uint32_t k, tile;
+            locate(n, g, k, tile);
+            const unsigned long long b = (unsigned long long)tile * TILE + t;
+            const uint32_t* s0 = s_csr.in[MM * k + j] + b * 16;
+            const uint32_t* s1 = s_csr.in[MM * k + j + 1] + b * 16;
+            x0 = fr::load_stream(s0);
+            y0 = fr::load_stream(s0 + 8);
+            x1 = fr::load_stream(s1);
+            y1 = fr::load_stream(s1 + 8);
+        };
+        Fr a0, b0, a1, b1, na0, nb0, na1, nb1;
+        if (n_items) fetch(0, 0, a0, b0, a1, b1);
+        for (uint32_t n = 0; n < n_items; n++) {
+            Fr a2, b2, a3, b3;
+            if (MM == 4) fetch(n, 2, a2, b2, a3, b3);
+            // the next item's pairs are requested before this item's products are computed: a group always has loads in flight
+            if (n + 1 < n_items) fetch(n + 1, 0, na0, nb0, na1, nb1);
+            if (n > 0) tcf::mbar_wait(&x_empty[g], (n - 1) & 1u);  // the contraction of item n-1 has read the operands
+            products_to_smem(a0, b0, a1, b1, base + L::XA, base + L::XQ, t);
+            if (MM == 4) y_products_to_smem(a2, b2, a3, b3, base + L::Y0, t);
+            a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
+            tcf::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tcf::mbar_arrive(&x_full[g]);
+        }
+    } else if (warp == G * 4) {
+        // ---------------------------------------------------------------------------------------------------- TMA of the Y tiles (MM = 3)
+        if (MM == 3 && lane == 0) {
+            const uint32_t steps = sp.steps();
+            for (uint32_t n = 0; n < steps; n++) {
+                const uint32_t ng = sp.groups(n);
+#pragma unroll
+                for (uint32_t g = 0; g < (uint32_t)G; g++) {
+                    if (g >= ng) continue;
+                    const uint32_t s = n & 1u;
+                    if (n >= 2) tcf::mbar_wait(&y_empty[g][s], ((n >> 1) - 1u) & 1u);
+                    uint32_t k, tile;
+                    locate(n, g, k, tile);
+                    tcf::mbar_expect_tx(&y_full[g][s], 8192);
+                    tcf::tma_load_tile(smem + (size_t)g * L::GROUP + (s ? L::Y1 : L::Y0), (const uint8_t*)P.ymaps + (size_t)s_csr.idx[MM * k + 2] * 128,
+                                       &y_full[g][s], tile * TILE);
+                }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------------------------------------- contraction MMAs
+        if (lane == 0) {
+            uint32_t acc = 0;
+            const uint32_t steps = sp.steps();
+            for (uint32_t n = 0; n < steps; n++) {
+                const uint32_t ng = sp.groups(n);
+#pragma unroll
+                for (uint32_t g = 0; g < (uint32_t)G; g++) {
+                    if (g >= ng) continue;
+                    const uint32_t s = MM == 3 ? (n & 1u) : 0u, gb = tcf::smem_u32(smem + (size_t)g * L::GROUP);
+                    if (MM == 3) tcf::mbar_wait(&y_full[g][s], (n >> 1) & 1u);
+                    tcf::mbar_wait(&x_full[g], n & 1u);
+                    tcf::tc_fence_after();
+                    issue_contraction<MM>(gb + L::XA, gb + L::XQ, gb + (s ? L::Y1 : L::Y0), tmem, acc);
+                    acc = 1;
+                    tcf::umma_commit(&x_empty[g]);
+                    if (MM == 3) tcf::umma_commit(&y_empty[g][s]);
+                }
+            }
+            // every MMA has completed once the last commit of every group has arrived
+#pragma unroll
+            for (uint32_t g = 0; g < (uint32_t)G; g++)
+                if (sp.n_items(g)) tcf::mbar_wait(&x_empty[g], (sp.n_items(g) - 1) & 1u);
+        }
+    }
+    __syncwarp();
+    tcf::tc_fence_before();
+    __syncthreads();
+    epilogue<MM>(P, tmem, sp.n_items(0) > 0, s_E, &s_last, reinterpret_cast<uint32_t*>(smem));
+    __syncthreads();
+    if (warp == 0) tcf::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// ================================================================================================ fold rounds, degree 3
+// Every table tile (128 rows x 128 bytes = old[4b..4b+3]) goes HBM -> shared memory by TMA into a ring shared by the groups
+// (warp W_TMA); warp W_FOLD issues the fix_variables MMAs (tc_fold.cuh) into the owning group's accumulator (two per group,
+// alternating); the group's thread t reads out new[2b], new[2b+1] of pair b = tile * 128 + t, stores them (the folded table)
+// and, once it holds the pairs of the product's first two tables, writes the three plain products; the folded pair of the
+// third table is the Y operand; warp W_SUM issues the contraction MMAs.  Each producer warp walks the same sequence of units
+// (item n, multiplicand j, group g) — g innermost, so consecutive units belong to different groups — and never computes
+// anything but a ring slot and a barrier phase (a producer that also chased the product list through global memory cost
+// ~1700 cycles per unit and starved every group: measured).
+template <int G, int MM>
+struct FoldSmem {
+    static constexpr uint32_t RING_SLOTS = 6;
+    static constexpr uint32_t GROUPS = RING_SLOTS * tcf::TILE_BYTES;
+    static constexpr uint32_t XA = 0, XQ = 16384, Y = 24576, GROUP = Y + Shape<MM>::Y_BYTES;
+    static constexpr uint32_t BMAT = GROUPS + G * GROUP;
+    static constexpr size_t BYTES = (size_t)BMAT + tcf::BMAT_BYTES;
+};
+
+// Tensor memory: 2 N columns of contraction accumulators, then NACC fix_variables accumulators of 64 columns per group — MM = 3: three
+// groups x two (alternating), MM = 4: two groups x one (the 384 contraction columns leave room for two; a group's compute per table
+// tile is several times the latency of its MMAs, so one accumulator per group does not starve it).  512 columns either way.
+template <int G, int MM>
 __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params P) {
-    using L = FoldSmem<G>;
+    using L = FoldSmem<G, MM>;
+    using S_ = Shape<MM>;
     constexpr uint32_t R = L::RING_SLOTS;
     constexpr uint32_t W_TMA = G * 4, W_FOLD = G * 4 + 1, W_SUM = G * 4 + 2;
+    constexpr uint32_t NACC = MM == 3 ? 2 : 1, ACC0 = 2 * S_::N;
+    static_assert(ACC0 + G * NACC * 64 <= 512, "tensor memory");
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t slot_full[R], slot_empty[R], acc_full[G][2], acc_empty[G][2], x_full[G], x_empty[G];
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(8) uint32_t s_E[2 * NB3 * 96];
+    __shared__ __align__(8) uint32_t s_E[2 * S_::NB * S_::ES];
     __shared__ bool s_last;
     __shared__ CsrCache s_csr;
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const sck::RoundParams& p = P.rp;
     const long long t_start = P.prof ? clock64() : 0;
-    load_csr(s_csr, p, true);
+    load_csr<MM>(s_csr, p, true);
     uint8_t* const bmat = smem + L::BMAT;
     if (tid == 0) {
         if (tcf::smem_u32(smem) & 1023u) __trap();
@@ -521,7 +569,7 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
         tcf::fence_proxy_async_smem();
         asm volatile("bar.arrive 1, 96;" ::: "memory");
     }
-    const Split<G> sp(P.items);
+    const Split<G, MM> sp(P.items);
     const bool one_product = p.n_products == 1;
     const bool pf = P.prof != nullptr && lane == 0;
     prof_mark(P.prof, 12, t_start);  // prologue done
@@ -529,7 +577,7 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
         // ---------------------------------------------------------------------------------------------------- compute group
         const uint32_t g = warp >> 2, t = tid & 127u;
         uint8_t* const base = smem + L::GROUPS + (size_t)g * L::GROUP;
-        const uint32_t lane_taddr = tmem + 128u + g * 128u + (((warp & 3u) * 32u) << 16);
+        const uint32_t lane_taddr = tmem + ACC0 + g * NACC * 64u + (((warp & 3u) * 32u) << 16);
         const uint32_t n_items = sp.n_items(g);
         ProfTimer t_acc, t_x, t_all;
         t_all.start(pf);
@@ -539,10 +587,10 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
             const unsigned long long b = (unsigned long long)tile * TILE + t;
             Fr e0, o0;
 #pragma unroll
-            for (uint32_t j = 0; j < 3; j++) {
-                const uint32_t q = 3 * n + j, a = q & 1u;
+            for (uint32_t j = 0; j < (uint32_t)MM; j++) {
+                const uint32_t q = MM * n + j, a = q % NACC;
                 t_acc.start(pf);
-                tcf::mbar_wait(&acc_full[g][a], (q >> 1) & 1u);
+                tcf::mbar_wait(&acc_full[g][a], (q / NACC) & 1u);
                 t_acc.stop(pf);
                 // the fold MMAs of this unit have completed: its ring slot is free again
                 if ((warp & 3u) == 0 && lane == 0) tcf::mbar_arrive(&slot_empty[sp.unit(n, j, g) % R]);
@@ -557,12 +605,12 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
                 __syncwarp();
                 if (lane == 0) tcf::mbar_arrive(&acc_empty[g][a]);
                 const Fr v1 = tcf::columns_to_fr(S);
-                if (s_csr.first[3 * k + j]) {
-                    uint32_t* dst = s_csr.out[3 * k + j] + b * 16;
+                if (s_csr.first[MM * k + j]) {
+                    uint32_t* dst = s_csr.out[MM * k + j] + b * 16;
                     fr::store(dst, v0);
                     fr::store(dst + 8, v1);
                 }
-                if (j == 0) {
+                if (j == 0 || (MM == 4 && j == 2)) {
                     e0 = v0;
                     o0 = v1;
                 } else if (j == 1) {
@@ -570,6 +618,8 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
                     if (n > 0) tcf::mbar_wait(&x_empty[g], (n - 1) & 1u);  // the contraction of item n-1 has read X and Y
                     t_x.stop(pf);
                     products_to_smem(e0, o0, v0, v1, base + L::XA, base + L::XQ, t);
+                } else if (MM == 4) {
+                    y_products_to_smem(e0, o0, v0, v1, base + L::Y, t);
                 } else {
                     uint32_t y[16];
 #pragma unroll
@@ -596,7 +646,7 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
             for (uint32_t n = 0; n < steps; n++) {
                 const uint32_t ng = sp.groups(n);
 #pragma unroll
-                for (uint32_t j = 0; j < 3; j++)
+                for (uint32_t j = 0; j < (uint32_t)MM; j++)
 #pragma unroll
                     for (uint32_t g = 0; g < (uint32_t)G; g++) {
                         if (g >= ng) continue;
@@ -607,7 +657,7 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
                         const uint32_t w = sp.item(n, g);
                         const uint32_t k = one_product ? 0u : w % p.n_products, tile = p.tile_base + (one_product ? w : w / p.n_products);
                         tcf::mbar_expect_tx(&slot_full[slot], tcf::TILE_BYTES);
-                        tcf::tma_load_tile(smem + (size_t)slot * tcf::TILE_BYTES, (const uint8_t*)p.tmaps + (size_t)s_csr.idx[3 * k + j] * 128, &slot_full[slot],
+                        tcf::tma_load_tile(smem + (size_t)slot * tcf::TILE_BYTES, (const uint8_t*)p.tmaps + (size_t)s_csr.idx[MM * k + j] * 128, &slot_full[slot],
                                            tile * TILE);
                         u++;
                     }
@@ -628,20 +678,20 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
             for (uint32_t n = 0; n < steps; n++) {
                 const uint32_t ng = sp.groups(n);
 #pragma unroll
-                for (uint32_t j = 0; j < 3; j++)
+                for (uint32_t j = 0; j < (uint32_t)MM; j++)
 #pragma unroll
                     for (uint32_t g = 0; g < (uint32_t)G; g++) {
                         if (g >= ng) continue;
-                        const uint32_t slot = u % R, q = 3 * n + j, a = q & 1u;
+                        const uint32_t slot = u % R, q = MM * n + j, a = q % NACC;
                         t_sf.start(pf);
                         tcf::mbar_wait(&slot_full[slot], (u / R) & 1u);
                         t_sf.stop(pf);
                         t_ae.start(pf);
-                        if (q >= 2) tcf::mbar_wait(&acc_empty[g][a], ((q >> 1) - 1u) & 1u);
+                        if (q >= NACC) tcf::mbar_wait(&acc_empty[g][a], ((q / NACC) - 1u) & 1u);
                         t_ae.stop(pf);
                         tcf::tc_fence_after();
                         t_mma.start(pf);
-                        tcf::issue_fold_mma(ring + slot * tcf::TILE_BYTES, bmat_smem, tmem + 128u + g * 128u + a * 64u);
+                        tcf::issue_fold_mma(ring + slot * tcf::TILE_BYTES, bmat_smem, tmem + ACC0 + (g * NACC + a) * 64u);
                         tcf::umma_commit(&acc_full[g][a]);
                         t_mma.stop(pf);
                         u++;
@@ -667,7 +717,7 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
                     t_xf.stop(pf);
                     tcf::tc_fence_after();
                     t_iss.start(pf);
-                    issue_contraction(gb + L::XA, gb + L::XQ, gb + L::Y, tmem, acc);
+                    issue_contraction<MM>(gb + L::XA, gb + L::XQ, gb + L::Y, tmem, acc);
                     acc = 1;
                     tcf::umma_commit(&x_empty[g]);
                     t_iss.stop(pf);
@@ -683,18 +733,17 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
     __syncwarp();
     tcf::tc_fence_before();
     __syncthreads();
-    epilogue3(P, tmem, sp.n_items(0) > 0, s_E, &s_last, reinterpret_cast<uint32_t*>(smem), t_start);
+    epilogue<MM>(P, tmem, sp.n_items(0) > 0, s_E, &s_last, reinterpret_cast<uint32_t*>(smem), t_start);
     __syncthreads();
     if (warp == 0) tcf::tmem_dealloc(tmem, 512);
 }
 
 // ---- launchers (gemm.cu) ------------------------------------------------------------------------------------------------------------
 cudaError_t init_constants();
-int groups_round1();
-int groups_fold();
-unsigned long long max_items_round1(int sms);  // work items one launch may carry (s32 accumulator head-room)
-unsigned long long max_items_fold(int sms);
-cudaError_t launch_round1(const Params& P, int sms, cudaStream_t stream);
-cudaError_t launch_fold(const Params& P, int sms, cudaStream_t stream);
+// mm = multiplicands per product (3 or 4)
+unsigned long long max_items_round1(int sms, int mm);  // work items one launch may carry (s32 accumulator head-room)
+unsigned long long max_items_fold(int sms, int mm);
+cudaError_t launch_round1(const Params& P, int mm, int sms, cudaStream_t stream);
+cudaError_t launch_fold(const Params& P, int mm, int sms, cudaStream_t stream);
 
 }  // namespace gsum

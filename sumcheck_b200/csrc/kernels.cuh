@@ -615,8 +615,8 @@ __device__ __forceinline__ void publish_round(const RoundParams& p, const Fr (&a
 #define SC_THREADS 128
 #endif
 constexpr int ROUND_THREADS = SC_THREADS;  // CTA size of round_kernel in this translation unit
-constexpr uint32_t MAIL_WORDS = 512;  // per (slot, rank): up to 256 {value, sequence number} pairs — 6 points x 8 limbs, 5 x 17 limbs of unreduced sums, or
-                                      // the 6 x 26 limbs of a contraction round (gemm_sum.cuh)
+constexpr uint32_t MAIL_WORDS = 1024;  // per (slot, rank): up to 512 {value, sequence number} pairs — 6 points x 8 limbs, 5 x 17 limbs of unreduced sums, or
+                                       // the 6 x 26 / 9 x 34 limbs of a contraction round (gemm_sum.cuh)
 constexpr uint32_t MAIL_SLOTS = 64;
 
 // One mailbox word = {limb, sequence number} packed into ONE 64-bit register and moved with a scalar 8-byte access.  The

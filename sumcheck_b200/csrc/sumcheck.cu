@@ -277,6 +277,7 @@ struct sc_prover {
     uint64_t launches = 0, tc_rounds = 0, res_rounds = 0, gemm_rounds = 0;
     // Tensor-core contraction rounds (gemm_sum.cuh): products of three tables; the sums arrive as big integers in h_gemm
     bool gemm_shape = false;     // the list of products has the shape those kernels serve
+    uint32_t gemm_m = 0;         // ... every product has gemm_m multiplicands (3 or 4)
     bool gemm_r1_ok = false;     // ... and the 64-byte-row descriptors of the pristine tables exist (round 1)
     bool gemm_active = false;    // the round just issued delivers through h_gemm
     uint8_t* d_ymaps = nullptr;  // [T] CUtensorMap: tab0 as rows of one pair (64 bytes), SWIZZLE_64B, 128-row boxes
@@ -427,7 +428,8 @@ int multi_table(const sc_prover* P, uint32_t j, uint64_t* out, uint64_t cap_elem
 inline const sc_prover* lead(const sc_prover* p) { return (p && !p->group.empty()) ? p->group[0] : p; }
 
 // ---- tensor-core contraction rounds (gemm_sum.cuh) --------------------------------------------------------------------------------
-constexpr uint32_t GEMM_LIMBS3 = gsum::OUT_LIMBS3, GEMM_NB3 = gsum::NB3;
+inline uint32_t gemm_limbs(const sc_prover* p) { return p->gemm_m == 4 ? gsum::Shape<4>::OUT_LIMBS : gsum::Shape<3>::OUT_LIMBS; }
+inline uint32_t gemm_nb(const sc_prover* p) { return p->gemm_m == 4 ? gsum::Shape<4>::NB : gsum::Shape<3>::NB; }
 
 // May this round (n_pairs output pairs; fold = rounds >= 2) run on the contraction kernels?
 bool gemm_round_ok(const sc_prover* p, unsigned long long n_pairs, bool fold) {
@@ -454,7 +456,8 @@ int launch_gemm_round(sc_prover* p, const sck::RoundParams& rp, bool fold, unsig
     G.rp.host_flag = G.rp.host_out + gsum::OUT_SLOT_WORDS - 1;
     G.rp.seq = seq;
     const int sms = g_dev[p->device].sms;
-    unsigned long long cap = (fold ? gsum::max_items_fold(sms) : gsum::max_items_round1(sms)) / p->n_products;  // tiles per launch
+    const int mm = (int)p->gemm_m;
+    unsigned long long cap = (fold ? gsum::max_items_fold(sms, mm) : gsum::max_items_round1(sms, mm)) / p->n_products;  // tiles per launch
     if (const char* env = getenv("SC_GEMM_MAX_TILES")) {  // tests: force the several-launches-per-round path at small sizes
         const unsigned long long v = strtoull(env, nullptr, 10);
         if (v >= 1 && v < cap) cap = v;
@@ -473,7 +476,7 @@ int launch_gemm_round(sc_prover* p, const sck::RoundParams& rp, bool fold, unsig
             cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), p->stream);
             G.prof = d_prof;
         }
-        cudaError_t e = fold ? gsum::launch_fold(G, sms, p->stream) : gsum::launch_round1(G, sms, p->stream);
+        cudaError_t e = fold ? gsum::launch_fold(G, mm, sms, p->stream) : gsum::launch_round1(G, mm, sms, p->stream);
         if (e != cudaSuccess) return fail(SC_ERR_CUDA, "contraction kernel launch: %s", cudaGetErrorString(e));
         if (prof) {
             long long h[16];
@@ -778,14 +781,15 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
         }
     }
     {
-        // Tensor-core contraction rounds (gemm_sum.cuh): every product has exactly three multiplicands; with several products
-        // every coefficient must already live in a table (checked per round: gemm_round_ok)
-        bool shape = d == 3 && !getenv("SC_NO_GEMM") && !getenv("SC_NO_TC");
-        for (uint32_t k = 0; k < n_products && shape; k++) shape = offsets[k + 1] - offsets[k] == 3;
+        // Tensor-core contraction rounds (gemm_sum.cuh): every product has exactly three (d = 3) or exactly four (d = 4)
+        // multiplicands; with several products every coefficient must already live in a table (checked per round: gemm_round_ok)
+        bool shape = (d == 3 || d == 4) && !getenv("SC_NO_GEMM") && !getenv("SC_NO_TC") && !(d == 4 && getenv("SC_NO_GEMM4"));
+        for (uint32_t k = 0; k < n_products && shape; k++) shape = offsets[k + 1] - offsets[k] == d;
         p->gemm_shape = shape;
+        p->gemm_m = shape ? d : 0;
         if (shape && N / 2 >= gsum::TILE) {
             p->h_ymaps.resize(T);
-            bool ok = true;
+            bool ok = true;  // (only three-table products read a table through these descriptors: the Y operand of round 1)
             for (uint32_t j = 0; j < T && ok; j++) ok = tmaph::make_pair_map(&p->h_ymaps[j], p->tab0[j], N / 2, gsum::TILE);
             p->gemm_r1_ok = ok;
             if (ok) TRY_P(cudaMemcpyAsync(p->d_ymaps, p->h_ymaps.data(), (size_t)T * sizeof(CUtensorMap), cudaMemcpyHostToDevice, p->stream));
@@ -1020,8 +1024,8 @@ int sharded_round(sc_prover* p, const uint64_t* r);  // capi_multi.inc
 void host_finish_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
     const uint32_t d = p->d, ns = w->raw_npts;
     hfr::F sums[8], out[8], coeff;
-    if (w->gemm_active) {  // six big integers from the contraction kernels -> P(0..d)
-        hfr::gemm_finish(w->h_gemm, GEMM_LIMBS3, 2, 1, d, out);
+    if (w->gemm_active) {  // the big integers from the contraction kernels (six at degree 3, nine at degree 4) -> P(0..d)
+        hfr::gemm_finish(w->h_gemm, gemm_limbs(p), 2, p->gemm_m - 2, d, out);
         if (p->n_products == 1) {
             memcpy(&coeff, p->h_coeffs.data(), 32);
             for (uint32_t t = 0; t <= d; t++) out[t] = hfr::mul(out[t], coeff);
@@ -1085,8 +1089,16 @@ uint32_t resident_first_round(const sc_prover* p) {
     // kernel); the replicated rounds after the switch run on the sub-prover's own resident launch
     if (p->comm && !comm_fused_exchange_ok(p)) return 0;
     const uint32_t last = p->comm ? p->switch_round - 1 : p->nv_local;
+    // The resident kernel multiplies on the CUDA cores, so a round costs it time in proportion to the entries of the product list;
+    // where the contraction kernels are available (a launch of theirs costs ~25-40 us whatever the list) the hand-over moves to
+    // smaller rounds for long lists: 2^16 pairs for one product of three tables, 2^13 for BASELINE config 4 (16 entries)
+    unsigned long long max_pairs = p->res_max_pairs;
+    if (p->gemm_shape && p->h_nnz > 3 && !getenv("SC_RES_MAX_PAIRS")) {
+        max_pairs = max_pairs * 3 / p->h_nnz;
+        if (max_pairs < p->tc_min_pairs / 2) max_pairs = p->tc_min_pairs / 2;  // (rounds below tc_min_pairs have no launch of their own to go to)
+    }
     for (uint32_t i = 2; i <= last; i++)
-        if (((unsigned long long)1 << (p->nv_local - i)) <= p->res_max_pairs) return i;
+        if (((unsigned long long)1 << (p->nv_local - i)) <= max_pairs) return i;
     return 0;
 }
 
@@ -1305,10 +1317,11 @@ int prove_round_issue(sc_prover* p, const uint64_t* r_or_null) {
         __sync_synchronize();
         const uint32_t npts = p->d + 1;
         if (p->eager_gemm) {  // add the chunks' integers up in slot 0
-            memset(p->h_gemm, 0, (size_t)GEMM_NB3 * GEMM_LIMBS3 * 4);
+            const uint32_t nb = gemm_nb(p), nl = gemm_limbs(p);
+            memset(p->h_gemm, 0, (size_t)nb * nl * 4);
             for (uint32_t c = 0; c < EAGER_CHUNKS; c++)
-                for (uint32_t i = 0; i < GEMM_NB3; i++)
-                    hfr::add_limbs(p->h_gemm + (size_t)i * GEMM_LIMBS3, p->h_gemm + (size_t)(1 + c) * gsum::OUT_SLOT_WORDS + (size_t)i * GEMM_LIMBS3, GEMM_LIMBS3);
+                for (uint32_t i = 0; i < nb; i++)
+                    hfr::add_limbs(p->h_gemm + (size_t)i * nl, p->h_gemm + (size_t)(1 + c) * gsum::OUT_SLOT_WORDS + (size_t)i * nl, nl);
             p->gemm_active = true;
             p->gemm_rounds++;
         } else {

@@ -339,29 +339,34 @@ def test_tensor_core_fold_special_values_and_edge_challenges(orc, monkeypatch):
     assert st.tc_round_count() == 2   # rounds 2 and 3 of nv=10 (256 and 128 output pairs)
 
 
-@pytest.mark.parametrize("nv,n_products,shared,max_tiles", [
-    (8, 1, False, None),     # one tile: round 1 only
-    (9, 1, False, None),     # round 1 = two tiles, round 2 = one tile (fold)
-    (11, 1, True, None),     # one product over a shared pool: repeated tables inside the product
-    (13, 1, False, None),    # more tiles than one group handles at once
-    (12, 3, False, None),    # three products of three fresh tables each: coefficients pre-scaled into tables
-    (13, 2, False, 3),       # a round split over several launches (the s32 accumulators' head-room), 3 tiles per launch
-    (12, 4, True, None),     # shared tables between products: nothing to pre-scale, must fall back and still agree
+@pytest.mark.parametrize("nv,n_products,shared,max_tiles,m", [
+    (8, 1, False, None, 3),     # one tile: round 1 only
+    (9, 1, False, None, 3),     # round 1 = two tiles, round 2 = one tile (fold)
+    (11, 1, True, None, 3),     # one product over a shared pool: repeated tables inside the product
+    (13, 1, False, None, 3),    # more tiles than one group handles at once
+    (12, 3, False, None, 3),    # three products of three fresh tables each: coefficients pre-scaled into tables
+    (13, 2, False, 3, 3),       # a round split over several launches (the s32 accumulators' head-room), 3 tiles per launch
+    (12, 4, True, None, 3),     # shared tables between products: nothing to pre-scale, must fall back and still agree
+    (8, 1, False, None, 4),     # products of FOUR tables: both operands of the contraction are plain products (192 x 192)
+    (10, 1, True, None, 4),
+    (13, 1, False, None, 4),
+    (12, 4, False, None, 4),    # the shape of BASELINE config 4: four products of four fresh tables
+    (13, 2, False, 5, 4),
 ])
-def test_contraction_rounds(orc, monkeypatch, nv, n_products, shared, max_tiles):
-    """Degree-3 products on the tensor-core contraction kernels (csrc/gemm_sum.cuh): three plain products per pair, the sum over
-    the pairs as a u8 x u8 -> s32 tcgen05.mma, six big integers to the host.  Same bytes as the oracle, the same folded tables
-    (assert_same_proof), and identical to the previous kernels (SC_NO_GEMM=1)."""
+def test_contraction_rounds(orc, monkeypatch, nv, n_products, shared, max_tiles, m):
+    """Products of three (or four) tables on the tensor-core contraction kernels (csrc/gemm_sum.cuh): plain products per pair, the
+    sum over the pairs as a u8 x u8 -> s32 tcgen05.mma, six (nine) big integers to the host.  Same bytes as the oracle, the same
+    folded tables (assert_same_proof), and identical to the previous kernels (SC_NO_GEMM=1)."""
     import ctypes as C
     monkeypatch.setenv("SC_TC_MIN_PAIRS", "128")
     monkeypatch.setenv("SC_RES_MAX_PAIRS", "64")
     if max_tiles:
         monkeypatch.setenv("SC_GEMM_MAX_TILES", str(max_tiles))
-    tables, products = random_instance(9100 + 17 * nv + n_products, nv, n_products, (3, 4), shared)
+    tables, products = random_instance(9100 + 17 * nv + n_products + 1000 * m, nv, n_products, (m, m + 1), shared)
     poly, opoly = both_polys(orc, nv, tables, products)
     got, rand = assert_same_proof(orc, poly, opoly)
     st = sc.IPForMLSumcheck.prover_init(poly)
-    ev = np.zeros((nv, 4, 4), dtype=np.uint64)
+    ev = np.zeros((nv, m + 1, 4), dtype=np.uint64)
     rng = sc.Blake2b512Rng.setup()
     assert sc.lib().sc_ml_prove(st._h, C.byref(rng.state), ev.ctypes.data_as(sc.capi.U64P), None) == 0
     assert np.array_equal(ev, got)
@@ -377,16 +382,17 @@ def test_contraction_rounds(orc, monkeypatch, nv, n_products, shared, max_tiles)
     assert np.array_equal(ev2, ev)
 
 
-def test_contraction_rounds_special_values_and_edge_challenges(orc, monkeypatch):
+@pytest.mark.parametrize("m", [3, 4])
+def test_contraction_rounds_special_values_and_edge_challenges(orc, monkeypatch, m):
     """0 / 1 / p-1 / all-0xff-byte tables and the challenges 0, 1, p-1 through the interactive API (sc_prove_round), folded tables
     compared with the oracle after every round: extreme bytes in both MMA operands, extreme carries in the plain products."""
     monkeypatch.setenv("SC_TC_MIN_PAIRS", "128")
     nv = 11
     rnd = random.Random(12)
     pool = [0, 1, pm.P - 1, 2, pm.P - 2, (1 << 248) - 1, pm.P >> 1]
-    tables = [[rnd.choice(pool) for _ in range(1 << nv)] for _ in range(3)]
+    tables = [[rnd.choice(pool) for _ in range(1 << nv)] for _ in range(m)]
     tables[2] = [pm.P - 1] * (1 << nv)   # Montgomery form of p-1 and near-maximal products everywhere
-    products = [(pm.P - 1, [0, 1, 2])]
+    products = [(pm.P - 1, list(range(m)))]
     poly, opoly = both_polys(orc, nv, tables, products)
     st, ost = sc.IPForMLSumcheck.prover_init(poly), orc.Prover(opoly)
     chal = [0, 1, pm.P - 1, rnd.randrange(pm.P)]

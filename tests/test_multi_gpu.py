@@ -78,15 +78,15 @@ def test_single_process_sharded_contraction_rounds(orc, monkeypatch, world):
     monkeypatch.setenv("SC_RES_MAX_PAIRS", "64")
     monkeypatch.setenv("SC_REPL_LOG2", "8")   # stay sharded until the global tables are down to 2^8 elements
     devs = _devices(world)
-    for nv, n_products, seed in [(12, 1, 41), (13, 3, 42)]:
-        tabs, prods = _instance(orc, nv, n_products, 3, seed)
+    for nv, n_products, seed, m in [(12, 1, 41, 3), (13, 3, 42, 3), (12, 2, 43, 4)]:
+        tabs, prods = _instance(orc, nv, n_products, m, seed)
         poly = sc.ListOfProductsOfPolynomials.new(nv)
         for c, ix in prods:
             poly.add_product([tabs[j] for j in ix], c)
         st = sc.IPForMLSumcheck.prover_init(poly, device=devs)
         want, rand, fin = orc.ml_prove(orc.Poly(nv, tabs, prods))
         for rep in range(2):
-            ev = np.zeros((nv, 4, 4), dtype=np.uint64)
+            ev = np.zeros((nv, m + 1, 4), dtype=np.uint64)
             st.prove_into(sc.Blake2b512Rng.setup(), ev)
             assert np.array_equal(ev, want), f"world {world} nv {nv} rep {rep}"
             assert st.gemm_round_count() >= 3

@@ -18,8 +18,8 @@
 
 constexpr uint32_t PAIRS = 128;
 
-__device__ __forceinline__ uint64_t mn_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
-    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
+__device__ __forceinline__ uint64_t mn_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type, uint32_t lbo_bytes = 16) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)layout_type << 61);
 }
 __device__ __forceinline__ uint32_t idesc_u8_mn(uint32_t M, uint32_t N) {
@@ -121,6 +121,61 @@ __global__ void __launch_bounds__(128) gemmsum_test_kernel(const CUtensorMap* ym
     if (warp == 0) tcf::tmem_dealloc(taddr, 256);
 }
 
+//   D5  A = XA (M = 128), B = three [128 pairs][64 B] SWIZZLE_64B arrays 8 KiB apart = N 192 through the leading byte offset
+//   D6  A = XB (M = 64),  same B
+__global__ void __launch_bounds__(128) gemmsum_wide_kernel(const uint8_t* xbytes /* [128][192] */, const uint8_t* ybytes /* [128][192] */,
+                                                            uint32_t* dump /* [128 lanes][384 cols] */) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* XA = smem;             // 16 KB
+    uint8_t* XB = smem + 16384;     // 8 KB
+    uint8_t* Y3 = smem + 24576;     // 3 x 8 KB
+    __shared__ __align__(8) uint64_t bar_mma;
+    __shared__ uint32_t s_tmem;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        tcf::mbar_init(&bar_mma, 1);
+        tcf::fence_mbar_init();
+    }
+    if (warp == 0) tcf::tmem_alloc(&s_tmem, 512);
+    const uint8_t* xr = xbytes + (size_t)tid * 192;
+    const uint8_t* yr = ybytes + (size_t)tid * 192;
+#pragma unroll
+    for (uint32_t c = 0; c < 8; c++) *reinterpret_cast<uint4*>(XA + tid * 128 + ((c ^ (tid & 7)) << 4)) = *reinterpret_cast<const uint4*>(xr + c * 16);
+#pragma unroll
+    for (uint32_t c = 0; c < 4; c++) {
+        *reinterpret_cast<uint4*>(XB + tid * 64 + ((c ^ ((tid >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(xr + 128 + c * 16);
+        for (uint32_t a = 0; a < 3; a++)
+            *reinterpret_cast<uint4*>(Y3 + a * 8192 + tid * 64 + ((c ^ ((tid >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(yr + a * 64 + c * 16);
+    }
+    tcf::fence_proxy_async_smem();
+    tcf::tc_fence_before();
+    __syncthreads();
+    tcf::tc_fence_after();
+    const uint32_t taddr = s_tmem;
+    if (tid == 0) {
+        const uint32_t i128 = idesc_u8_mn(128, 192), i64 = idesc_u8_mn(64, 192);
+        for (uint32_t ks = 0; ks < 4; ks++) {
+            const uint64_t b = mn_desc(tcf::smem_u32(Y3) + ks * 2048, 512, 4, 8192);
+            umma(taddr + 0, mn_desc(tcf::smem_u32(XA) + ks * 4096, 1024, 2), b, i128, ks);
+            umma(taddr + 192, mn_desc(tcf::smem_u32(XB) + ks * 2048, 512, 4), b, i64, ks);
+        }
+        tcf::umma_commit(&bar_mma);
+    }
+    tcf::mbar_wait(&bar_mma, 0);
+    tcf::tc_fence_after();
+    const uint32_t lane_addr = taddr + ((warp * 32u) << 16);
+    for (uint32_t c0 = 0; c0 < 384; c0 += 32) {
+        uint32_t S[32];
+        tcf::tmem_ld32(lane_addr + c0, S);
+        tcf::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j++) dump[(size_t)tid * 384 + c0 + j] = S[j];
+    }
+    tcf::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tcf::tmem_dealloc(taddr, 512);
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 2; } } while (0)
 
 int main() {
@@ -181,7 +236,36 @@ int main() {
     printf("256 MMAs M=128 N=64 K=32: issue %lld cycles, issue->done %lld (%.1f per MMA);  M=64: issue %lld, done %lld (%.1f per MMA)\n", clk[0], clk[1],
            clk[1] / 256.0, clk[2], clk[3], clk[3] / 256.0);
     printf("D1 (SW128 A, TMA SW64 B) bad=%d   D2 (M=64, SW64 A) rows not found=%d   D3 (M=128, half rows) bad=%d   D4 (hand-swizzled B) bad=%d\n", bad1, bad2, bad3, bad4);
-    const bool ok = !(bad1 | bad2 | bad3 | bad4);
+    // ---- N = 192 through the leading byte offset
+    int bad5 = 0, bad6 = 0;
+    {
+        std::vector<uint8_t> y3(PAIRS * 192);
+        for (auto& v : y3) v = rnd();
+        uint8_t* dy3; uint32_t* dd3;
+        CK(cudaMalloc(&dy3, y3.size())); CK(cudaMalloc(&dd3, 128 * 384 * 4));
+        CK(cudaMemcpy(dy3, y3.data(), y3.size(), cudaMemcpyHostToDevice));
+        const size_t smem3 = 49152 + 1024;
+        CK(cudaFuncSetAttribute(gemmsum_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        gemmsum_wide_kernel<<<1, 128, smem3>>>(dx, dy3, dd3);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        std::vector<uint32_t> d3(128 * 384);
+        CK(cudaMemcpy(d3.data(), dd3, d3.size() * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> W3(192 * 192, 0);
+        for (uint32_t k = 0; k < PAIRS; k++)
+            for (uint32_t r = 0; r < 192; r++)
+                for (uint32_t c = 0; c < 192; c++) W3[r * 192 + c] += (uint32_t)x[k * 192 + r] * y3[k * 192 + c];
+        for (uint32_t r = 0; r < 128; r++)
+            for (uint32_t c = 0; c < 192; c++)
+                if (d3[r * 384 + c] != W3[r * 192 + c] && bad5++ < 4) printf("  D5[%u][%u] got %u want %u\n", r, c, d3[r * 384 + c], W3[r * 192 + c]);
+        for (uint32_t r = 0; r < 64; r++) {
+            const uint32_t l = (r % 16) + 32 * (r / 16);
+            for (uint32_t c = 0; c < 192; c++)
+                if (d3[l * 384 + 192 + c] != W3[(128 + r) * 192 + c] && bad6++ < 4) printf("  D6[%u][%u] got %u want %u\n", r, c, d3[l * 384 + 192 + c], W3[(128 + r) * 192 + c]);
+        }
+        printf("D5 (M=128, N=192 as three SWIZZLE_64B atoms, LBO 8192) bad=%d   D6 (M=64, N=192) bad=%d\n", bad5, bad6);
+    }
+    const bool ok = !(bad1 | bad2 | bad3 | bad4 | bad5 | bad6);
     printf(ok ? "GEMMSUM OK\n" : "GEMMSUM FAIL\n");
     return ok ? 0 : 1;
 }
