@@ -301,8 +301,8 @@ def bench_ml(args, cfg, nv, dev):
     if tc_rounds:
         dom_bytes = sum(algorithmic_bytes(nv, T, i) for i in tc_rounds)
         dom_ms = float(sum(round_ms[i - 1] for i in tc_rounds))
-        dom_name = (f"gsum::gemm_fold_kernel<3> (TMA + tcgen05.mma fix_variables, three plain products per pair, tcgen05.mma contraction over the "
-                    f"pairs), rounds 2..{1 + n_tc} aggregated") if gemm else \
+        dom_name = (f"gsum::gemm_fold_kernel<{2 if d == 4 else 3}, {d}> (TMA + tcgen05.mma fix_variables, {3 if d == 3 else 6} plain products per pair, "
+                    f"tcgen05.mma contraction over the pairs), rounds 2..{1 + n_tc} aggregated") if gemm else \
                    f"sck::round_tc_kernel<{d}> (TMA + tcgen05.mma fold fused with the sum), rounds 2..{1 + n_tc} aggregated"
     else:  # small configs: everything after round 1 is the resident launch
         dom_bytes = sum(algorithmic_bytes(nv, T, i) for i in range(2, nv + 1))
@@ -328,7 +328,7 @@ def bench_ml(args, cfg, nv, dev):
                      "whole_proof": {"algorithmic_bytes": total_bytes, "achieved": total_bytes / (ms_step * 1e-3) / 1e9,
                                      "frac": total_bytes / (ms_step * 1e-3) / 1e9 / peak,
                                      "frac_of_8TBps_nominal": total_bytes / (ms_step * 1e-3) / 8e12},
-                     "round1": {"kernel": "gsum::gemm_round1_kernel<3>" if gemm else f"sck::round1_tma_kernel<{d + 1}>", "achieved": algorithmic_bytes(nv, T, 1) / (round_ms[0] * 1e-3) / 1e9,
+                     "round1": {"kernel": f"gsum::gemm_round1_kernel<3, {d}>" if gemm else f"sck::round1_tma_kernel<{d + 1}>", "achieved": algorithmic_bytes(nv, T, 1) / (round_ms[0] * 1e-3) / 1e9,
                                 "frac": algorithmic_bytes(nv, T, 1) / (round_ms[0] * 1e-3) / 1e9 / peak},
                      "resident_rounds_ms": res_ms,
                      "note": "traffic: see profiles/ (ncu dram bytes per launch); not re-measured inside bench.py"},

@@ -158,6 +158,14 @@ SC_API void sc_release_cached_memory(void);
  * same routine finishes every prover round: the device delivers the summed points and P(1) = P_prev(r) - P(0). */
 SC_API int sc_fr_interpolate(const uint64_t *evals, uint32_t n_evals, const uint64_t r[4], uint64_t out[4]);
 
+/* The host half of a tensor-core contraction round (csrc/gemm_sum.cuh, csrc/host_fr.h gemm_finish): a product of kx + ky tables
+ * (kx, ky in {1, 2}) is split into an X side and a Y side; a side of one table contributes the values (a, b) = (table[2b],
+ * table[2b+1]), a side of two tables the plain products (a a', b b', (a+b)(a'+b')).  z = the nx*ny integers sum_b X_i * Y_j
+ * (n_limbs 32-bit limbs each, row-major, plain products of Montgomery-form operands) as the device delivers them; out
+ * receives P(0..kx+ky), Montgomery form, before any coefficient: the unscaled round polynomial of prover.rs:110-148.
+ * Host-side scalar arithmetic (no GPU needed) — exposed so that it can be checked against the big-integer model on CPU. */
+SC_API int sc_fr_contraction_finish(const uint32_t *z, uint32_t n_limbs, uint32_t kx, uint32_t ky, uint64_t *out);
+
 /* ------------------------------------------------------------------------------------------------------------
  * GKRRoundSumcheck (src/gkr_round_sumcheck/mod.rs).  f1: SparseMultilinearExtension over 3*dim variables as nnz
  * (index, value) pairs with unique indices (its BTreeMap); index bits are g | x | y, least significant first

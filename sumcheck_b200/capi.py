@@ -54,6 +54,7 @@ SIGNATURES = {
     "sc_prover_gemm_round_count": (C.c_uint64, [C.c_void_p]),
     "sc_release_cached_memory": (None, []),
     "sc_fr_interpolate": (C.c_int, [U64P, C.c_uint32, U64P, U64P]),
+    "sc_fr_contraction_finish": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, U64P]),
     "sc_poly_evaluate": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32, U64P, U32P, U32P, U64P, C.c_int, U64P]),
     "sc_ml_verify": (C.c_int, [C.POINTER(RngState), C.c_uint32, C.c_uint32, U64P, U64P, C.c_int, U64P, U64P]),
     "sc_comm_get_unique_id": (C.c_int, [U8P]),

@@ -1861,6 +1861,13 @@ int sc_fr_interpolate(const uint64_t* evals, uint32_t n_evals, const uint64_t r[
     memcpy(out, &v, 32);
     return SC_OK;
 }
+int sc_fr_contraction_finish(const uint32_t* z, uint32_t n_limbs, uint32_t kx, uint32_t ky, uint64_t* out) {
+    if (!z || !out || kx < 1 || kx > 2 || ky < 1 || ky > 2 || n_limbs < 1 || n_limbs > 64) return fail(SC_ERR_BAD_INPUT, "contraction_finish: bad shape");
+    hfr::F ev[8];
+    hfr::gemm_finish(z, n_limbs, kx, ky, kx + ky, ev);
+    memcpy(out, ev, (size_t)(kx + ky + 1) * 32);
+    return SC_OK;
+}
 int sc_prover_set_timing(sc_prover* p, int enabled) {
     NEED_HANDLE(p);
     if (!p->group.empty()) {
