@@ -143,6 +143,109 @@ __device__ __forceinline__ void mul_plain(const Fr& a, const Fr& b, uint32_t (&o
         : "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]), "r"(od[8]), "r"(od[9]), "r"(od[10]),
           "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]), "r"(c0));
 }
+// ---- one-level Karatsuba: 3 x 16 = 48 IMAD.WIDE instead of 64, the glue (~65 adds) goes to the ALU pipe, which idles while the
+// multiply pipe is the binding unit of round 1 (ncu: 67 % against 17 %, profiles/r2c_ncu_full_rounds12_summary.txt)
+#ifndef SC_GEMM_KARATSUBA
+#define SC_GEMM_KARATSUBA 1
+#endif
+// z = a * b for 4-limb operands (8 limbs)
+__device__ __forceinline__ void mul4(const uint32_t (&a)[4], const uint32_t (&b)[4], uint32_t (&z)[8]) {
+    uint32_t ev[8], od[8];
+    fr::mul_wide_eo4(ev, od, a, b);
+    z[0] = ev[0];
+    asm("add.cc.u32 %0, %7, %14;\n\t"
+        "addc.cc.u32 %1, %8, %15;\n\t"
+        "addc.cc.u32 %2, %9, %16;\n\t"
+        "addc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\t"
+        "addc.cc.u32 %5, %12, %19;\n\t"
+        "addc.u32 %6, %13, %20;\n\t"
+        : "=r"(z[1]), "=r"(z[2]), "=r"(z[3]), "=r"(z[4]), "=r"(z[5]), "=r"(z[6]), "=r"(z[7])
+        : "r"(ev[1]), "r"(ev[2]), "r"(ev[3]), "r"(ev[4]), "r"(ev[5]), "r"(ev[6]), "r"(ev[7]), "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]),
+          "r"(od[4]), "r"(od[5]), "r"(od[6]));
+}
+// r = x + y (4 limbs), returns the carry
+__device__ __forceinline__ uint32_t add4(const uint32_t* x, const uint32_t* y, uint32_t (&r)[4]) {
+    uint32_t c;
+    asm("add.cc.u32 %0, %5, %9;\n\t"
+        "addc.cc.u32 %1, %6, %10;\n\t"
+        "addc.cc.u32 %2, %7, %11;\n\t"
+        "addc.cc.u32 %3, %8, %12;\n\t"
+        "addc.u32 %4, 0, 0;\n\t"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(c)
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]));
+    return c;
+}
+// o = a * b as a plain 512-bit integer: z0 = a_lo b_lo, z2 = a_hi b_hi, z1 = (a_lo + a_hi)(b_lo + b_hi) - z0 - z2
+__device__ __forceinline__ void mul_plain_karatsuba(const Fr& a, const Fr& b, uint32_t (&o)[16]) {
+    uint32_t alo[4] = {a.l[0], a.l[1], a.l[2], a.l[3]}, ahi[4] = {a.l[4], a.l[5], a.l[6], a.l[7]};
+    uint32_t blo[4] = {b.l[0], b.l[1], b.l[2], b.l[3]}, bhi[4] = {b.l[4], b.l[5], b.l[6], b.l[7]};
+    uint32_t z0[8], z2[8], zm[9], sa[4], sb[4];
+    mul4(alo, blo, z0);
+    mul4(ahi, bhi, z2);
+    const uint32_t ca = add4(alo, ahi, sa), cb = add4(blo, bhi, sb);
+    {
+        uint32_t t[8];
+        mul4(sa, sb, t);
+#pragma unroll
+        for (int i = 0; i < 8; i++) zm[i] = t[i];
+    }
+    // (sa + ca 2^128)(sb + cb 2^128) = sa sb + (ca sb + cb sa) 2^128 + ca cb 2^256
+    const uint32_t ma = 0u - ca, mb = 0u - cb;
+    asm("add.cc.u32 %0, %0, %5;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.cc.u32 %2, %2, %7;\n\t"
+        "addc.cc.u32 %3, %3, %8;\n\t"
+        "addc.u32 %4, %9, 0;\n\t"
+        : "+r"(zm[4]), "+r"(zm[5]), "+r"(zm[6]), "+r"(zm[7]), "=r"(zm[8])
+        : "r"(sb[0] & ma), "r"(sb[1] & ma), "r"(sb[2] & ma), "r"(sb[3] & ma), "r"(ca & cb));
+    asm("add.cc.u32 %0, %0, %5;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.cc.u32 %2, %2, %7;\n\t"
+        "addc.cc.u32 %3, %3, %8;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        : "+r"(zm[4]), "+r"(zm[5]), "+r"(zm[6]), "+r"(zm[7]), "+r"(zm[8])
+        : "r"(sa[0] & mb), "r"(sa[1] & mb), "r"(sa[2] & mb), "r"(sa[3] & mb));
+    // z1 = zm - z0 - z2 (non-negative, below 2^258: nine limbs)
+#define SC_SUB9(z)                                                                                                              \
+    asm("sub.cc.u32 %0, %0, %9;\n\t"                                                                                             \
+        "subc.cc.u32 %1, %1, %10;\n\t"                                                                                           \
+        "subc.cc.u32 %2, %2, %11;\n\t"                                                                                           \
+        "subc.cc.u32 %3, %3, %12;\n\t"                                                                                           \
+        "subc.cc.u32 %4, %4, %13;\n\t"                                                                                           \
+        "subc.cc.u32 %5, %5, %14;\n\t"                                                                                           \
+        "subc.cc.u32 %6, %6, %15;\n\t"                                                                                           \
+        "subc.cc.u32 %7, %7, %16;\n\t"                                                                                           \
+        "subc.u32 %8, %8, 0;\n\t"                                                                                                \
+        : "+r"(zm[0]), "+r"(zm[1]), "+r"(zm[2]), "+r"(zm[3]), "+r"(zm[4]), "+r"(zm[5]), "+r"(zm[6]), "+r"(zm[7]), "+r"(zm[8])      \
+        : "r"(z[0]), "r"(z[1]), "r"(z[2]), "r"(z[3]), "r"(z[4]), "r"(z[5]), "r"(z[6]), "r"(z[7]))
+    SC_SUB9(z0);
+    SC_SUB9(z2);
+#undef SC_SUB9
+    // o = z0 + z1 2^128 + z2 2^256
+    o[0] = z0[0]; o[1] = z0[1]; o[2] = z0[2]; o[3] = z0[3];
+    uint32_t c0;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;\n\t"
+        : "=r"(o[4]), "=r"(o[5]), "=r"(o[6]), "=r"(o[7]), "=r"(o[8]), "=r"(o[9]), "=r"(o[10]), "=r"(o[11]), "=r"(c0)
+        : "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]), "r"(z2[0]), "r"(z2[1]), "r"(z2[2]), "r"(z2[3]), "r"(zm[0]), "r"(zm[1]), "r"(zm[2]),
+          "r"(zm[3]), "r"(zm[4]), "r"(zm[5]), "r"(zm[6]), "r"(zm[7]));
+    asm("{ .reg .u32 t_; add.cc.u32 t_, %9, 0xffffffff; }\n\t"
+        "addc.cc.u32 %0, %4, %8;\n\t"
+        "addc.cc.u32 %1, %5, 0;\n\t"
+        "addc.cc.u32 %2, %6, 0;\n\t"
+        "addc.u32 %3, %7, 0;\n\t"
+        : "=r"(o[12]), "=r"(o[13]), "=r"(o[14]), "=r"(o[15])
+        : "r"(z2[4]), "r"(z2[5]), "r"(z2[6]), "r"(z2[7]), "r"(zm[8]), "r"(c0));
+}
+
 // a + b as a plain integer (both canonical: the sum is below 2p < 2^256)
 __device__ __forceinline__ Fr add_plain(const Fr& a, const Fr& b) {
     Fr r;
@@ -173,25 +276,32 @@ __device__ __forceinline__ void sts_sw64(uint8_t* base, uint32_t row, const uint
         *reinterpret_cast<uint4*>(base + row * 64u + ((c ^ ((row >> 1) & 3u)) << 4)) = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
 
+__device__ __forceinline__ void mul_plain_sel(const Fr& a, const Fr& b, uint32_t (&o)[16]) {
+#if SC_GEMM_KARATSUBA
+    mul_plain_karatsuba(a, b, o);
+#else
+    mul_plain(a, b, o);
+#endif
+}
 // The three products of one pair into the group's X operand: XA row = [q0 | q1] (SWIZZLE_128B), XQ row = qs (SWIZZLE_64B)
 __device__ __forceinline__ void products_to_smem(const Fr& a0, const Fr& b0, const Fr& a1, const Fr& b1, uint8_t* XA, uint8_t* XQ, uint32_t row) {
     uint32_t o[16];
-    mul_plain(a0, a1, o);
+    mul_plain_sel(a0, a1, o);
     sts_sw128(XA, row, 0, o);
-    mul_plain(b0, b1, o);
+    mul_plain_sel(b0, b1, o);
     sts_sw128(XA, row, 4, o);
-    mul_plain(add_plain(a0, b0), add_plain(a1, b1), o);
+    mul_plain_sel(add_plain(a0, b0), add_plain(a1, b1), o);
     sts_sw64(XQ, row, o);
 }
 
 // The three products of the Y side (MM = 4) into the group's three Y arrays
 __device__ __forceinline__ void y_products_to_smem(const Fr& a2, const Fr& b2, const Fr& a3, const Fr& b3, uint8_t* Y, uint32_t row) {
     uint32_t o[16];
-    mul_plain(a2, a3, o);
+    mul_plain_sel(a2, a3, o);
     sts_sw64(Y, row, o);
-    mul_plain(b2, b3, o);
+    mul_plain_sel(b2, b3, o);
     sts_sw64(Y + 8192, row, o);
-    mul_plain(add_plain(a2, b2), add_plain(a3, b3), o);
+    mul_plain_sel(add_plain(a2, b2), add_plain(a3, b3), o);
     sts_sw64(Y + 16384, row, o);
 }
 

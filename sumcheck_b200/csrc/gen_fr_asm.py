@@ -141,6 +141,26 @@ emit("}")
 emit("")
 
 # ---- accumulate variant: EV/OD hold running sums of several products; every chain propagates to the top limb.
+# ---- 4 x 4 limbs (128 x 128 bits): the building block of the one-level Karatsuba product of gemm_sum.cuh
+emit("// 128 x 128-bit product, same even/odd scheme: a*b = EV + OD*2^32 (ev[0..7], od[0..6]; od[7] = 0).")
+emit("__device__ __forceinline__ void mul_wide_eo4(uint32_t (&ev)[8], uint32_t (&od)[8], const uint32_t (&a)[4], const uint32_t (&b)[4]) {")
+emit("    od[7] = 0;")
+WRITTEN = {"ev": set(), "od": set()}
+A4_EVEN = ["a[0]", "a[2]"]
+A4_ODD = ["a[1]", "a[3]"]
+chain("ev", 0, 2, A4_EVEN, "b[0]", -1, first_is_mul=True)
+chain("od", 0, 2, A4_ODD, "b[0]", -1, first_is_mul=True)
+for i in range(1, 4):
+    if i % 2 == 1:
+        chain("od", i - 1, 2, A4_EVEN, f"b[{i}]", i + 3)
+        chain("ev", i + 1, 2, A4_ODD, f"b[{i}]", -1)
+    else:
+        chain("ev", i, 2, A4_EVEN, f"b[{i}]", i + 4)
+        chain("od", i, 2, A4_ODD, f"b[{i}]", -1)
+assert WRITTEN["ev"] == set(range(8)) and WRITTEN["od"] == set(range(7)), WRITTEN
+WRITTEN = None
+emit("}")
+emit("")
 emit("// ev/od (17 limbs each: 16 + one overflow limb) += a*b.  For lazily reduced inner products.")
 emit("__device__ __forceinline__ void mac_wide_eo(uint32_t (&ev)[17], uint32_t (&od)[17], const uint32_t (&a)[8], const uint32_t (&b)[8]) {")
 for i in range(8):
