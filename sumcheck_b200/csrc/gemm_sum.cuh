@@ -143,10 +143,12 @@ __device__ __forceinline__ void mul_plain(const Fr& a, const Fr& b, uint32_t (&o
         : "r"(ev[9]), "r"(ev[10]), "r"(ev[11]), "r"(ev[12]), "r"(ev[13]), "r"(ev[14]), "r"(ev[15]), "r"(od[8]), "r"(od[9]), "r"(od[10]),
           "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]), "r"(c0));
 }
-// ---- one-level Karatsuba: 3 x 16 = 48 IMAD.WIDE instead of 64, the glue (~65 adds) goes to the ALU pipe, which idles while the
-// multiply pipe is the binding unit of round 1 (ncu: 67 % against 17 %, profiles/r2c_ncu_full_rounds12_summary.txt)
+// ---- one-level Karatsuba: 3 x 16 = 48 IMAD.WIDE instead of 64, the glue (~65 adds) on the ALU pipe, which idles while the multiply
+// pipe is the binding unit of round 1 (ncu: 67 % against 17 %).  MEASURED SLOWER and therefore off: bit-exact, but round 1 0.343 ->
+// 0.354 ms, round 2 0.394 -> 0.414 ms, config 4 2.45 -> 2.72 ms — the kernels are short of issue slots and latency hiding (12 warps
+// per SM), not of multiplier throughput alone, and ptxas leaves 32 of the 144 products unfused (IMAD + IMAD.HI).  Kept as a switch.
 #ifndef SC_GEMM_KARATSUBA
-#define SC_GEMM_KARATSUBA 1
+#define SC_GEMM_KARATSUBA 0
 #endif
 // z = a * b for 4-limb operands (8 limbs)
 __device__ __forceinline__ void mul4(const uint32_t (&a)[4], const uint32_t (&b)[4], uint32_t (&z)[8]) {
