@@ -60,6 +60,15 @@ struct Params {
     uint32_t publish;             // 0: only add into totals (a round split over several launches), 1: the last CTA publishes
     uint32_t items;               // work items (tile, product) of this launch
     long long* prof;              // SC_GEMM_PROF=1: [16] cycle counters summed over the CTAs (waits per role), else null
+    // A fold round launched AHEAD of its challenge (the host launches round i+1 right behind round i and hashes round i's message
+    // while this kernel's prologue and first table tiles are already under way): the eight limbs of r arrive through mapped host
+    // memory as {limb, sequence number} words, as in the resident kernel.  Null: r is in rp.r.
+    const unsigned long long* r_mail;
+    unsigned long long* r_bcast;  // device memory: CTA 0 alone polls the host (1184 threads polling over PCIe delay the very write they
+                                  // wait for by ~100 us: measured) and re-publishes the words here for the other CTAs
+    uint32_t r_seq;
+    long long r_timeout;          // clock64 ticks before the kernel gives up (continues with r = 0 and raises *r_error)
+    uint32_t* r_error;            // mapped host word
 };
 
 // phase markers (SC_GEMM_PROF): max over the CTAs of the cycles since the CTA started, slots 12..
@@ -675,8 +684,33 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
     const uint32_t tmem = s_tmem;
     if (warp < 2) {   // ... while warps 0 and 1 expand the challenge into the constants matrix, which only the first
         Fr r;         // fix_variables MMA waits for (named barrier 1: these two warps arrive, the MMA-issuing warp syncs)
+        if (P.r_mail) {  // launched ahead of the challenge: wait for the host to send it
+            __shared__ uint32_t s_r[8];
+            if (tid < 8) {
+                unsigned long long w;
+                const long long t0 = clock64();
+                const unsigned long long* src = blockIdx.x == 0 ? P.r_mail + tid : P.r_bcast + tid;
+                for (;;) {
+                    if (blockIdx.x == 0) asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+                    else asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+                    if ((uint32_t)(w >> 32) == P.r_seq) break;
+                    if (clock64() - t0 > P.r_timeout) {
+                        *P.r_error = 1;
+                        w = (unsigned long long)P.r_seq << 32;  // (release the other CTAs too)
+                        break;
+                    }
+                    if (blockIdx.x != 0) __nanosleep(200);
+                }
+                if (blockIdx.x == 0) asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(P.r_bcast + tid), "l"(w) : "memory");
+                s_r[tid] = (uint32_t)w;
+            }
+            asm volatile("bar.sync 2, 64;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 8; i++) r.l[i] = p.r[i];
+            for (int i = 0; i < 8; i++) r.l[i] = s_r[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) r.l[i] = p.r[i];
+        }
         tcf::build_bmat(r, bmat);
         tcf::fence_proxy_async_smem();
         asm volatile("bar.arrive 1, 96;" ::: "memory");

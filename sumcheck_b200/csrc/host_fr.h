@@ -240,21 +240,46 @@ inline void side_weights(uint32_t k, long long t, F* w) {
         w[2] = from_i64(t * (1 - t));
     }
 }
-inline void gemm_finish(const uint32_t* z, uint32_t n_limbs, uint32_t kx, uint32_t ky, uint32_t d, F* out) {
-    const uint32_t nx = kx == 1 ? 2 : 3, ny = ky == 1 ? 2 : 3, m = kx + ky;
-    const F one_int = {{1, 0, 0, 0}};
-    F Z[9];
-    for (uint32_t i = 0; i < nx * ny; i++) {
-        F v = reduce_limbs(z + (size_t)i * n_limbs, n_limbs);      // value * R^m mod p
-        for (uint32_t k = 1; k < m; k++) v = mul(v, one_int);      // -> value * R (Montgomery form)
-        Z[i] = v;
+// W[t][i * ny + j] = wX_i(t) * wY_j(t) * R^(2-m), so that mul(W, z) = weight * value * R for a raw residue
+// z = value * R^m: the weights, the division by R^(m-1) and the conversion cost ONE multiplication per (t, i, j).  Cached per
+// shape (this routine sits between two rounds of every proof: ~110 Montgomery multiplications before, ~50 now).
+struct GemmWeights {
+    F w[5][9];
+    uint32_t d = 0;
+};
+inline const GemmWeights& gemm_weights(uint32_t kx, uint32_t ky) {
+    static GemmWeights cache[3][3];
+    static bool ready[3][3] = {};
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    GemmWeights& g = cache[kx][ky];
+    if (!ready[kx][ky]) {
+        const uint32_t nx = kx == 1 ? 2 : 3, ny = ky == 1 ? 2 : 3, m = kx + ky;
+        const F one_int = {{1, 0, 0, 0}};
+        g.d = m;
+        for (uint32_t t = 0; t <= m; t++) {
+            F wx[3], wy[3];
+            side_weights(kx, (long long)t, wx);
+            side_weights(ky, (long long)t, wy);
+            for (uint32_t i = 0; i < nx; i++)
+                for (uint32_t j = 0; j < ny; j++) {
+                    F w = mul(wx[i], wy[j]);                                  // weight * R
+                    for (uint32_t k = 1; k < m; k++) w = mul(w, one_int);     // weight * R^(2-m): mul(w, z) = w z / R = weight * value * R
+                    g.w[t][i * ny + j] = w;
+                }
+        }
+        ready[kx][ky] = true;
     }
+    return g;
+}
+inline void gemm_finish(const uint32_t* z, uint32_t n_limbs, uint32_t kx, uint32_t ky, uint32_t d, F* out) {
+    const uint32_t nx = kx == 1 ? 2 : 3, ny = ky == 1 ? 2 : 3;
+    const GemmWeights& g = gemm_weights(kx, ky);
+    F Z[9];
+    for (uint32_t i = 0; i < nx * ny; i++) Z[i] = reduce_limbs(z + (size_t)i * n_limbs, n_limbs);  // value * R^m mod p (raw residue)
     for (uint32_t t = 0; t <= d; t++) {
-        F wx[3], wy[3], acc = {{0, 0, 0, 0}};
-        side_weights(kx, (long long)t, wx);
-        side_weights(ky, (long long)t, wy);
-        for (uint32_t i = 0; i < nx; i++)
-            for (uint32_t j = 0; j < ny; j++) acc = add(acc, mul(mul(wx[i], wy[j]), Z[i * ny + j]));
+        F acc = {{0, 0, 0, 0}};
+        for (uint32_t i = 0; i < nx * ny; i++) acc = add(acc, mul(g.w[t][i], Z[i]));
         out[t] = acc;
     }
 }

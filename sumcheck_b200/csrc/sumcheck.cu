@@ -280,6 +280,10 @@ struct sc_prover {
     uint32_t gemm_m = 0;         // ... every product has gemm_m multiplicands (3 or 4)
     bool gemm_r1_ok = false;     // ... and the 64-byte-row descriptors of the pristine tables exist (round 1)
     bool gemm_active = false;    // the round just issued delivers through h_gemm
+    uint32_t gemm_seq = 0, gemm_want = 0;  // flag values of the contraction launches: last handed out / the one the current round publishes
+    // a fold round launched ahead of its challenge (run_rounds only): its 1-based round number (0 = none) and its flag value
+    uint32_t gemm_pre_round = 0, gemm_pre_want = 0;
+    bool prelaunch_ok = false;   // inside a whole-proof call, where the next round always follows
     uint8_t* d_ymaps = nullptr;  // [T] CUtensorMap: tab0 as rows of one pair (64 bytes), SWIZZLE_64B, 128-row boxes
     std::vector<CUtensorMap> h_ymaps;
     unsigned long long* d_gemm_totals = nullptr;
@@ -446,10 +450,22 @@ bool gemm_round_ok(const sc_prover* p, unsigned long long n_pairs, bool fold) {
 
 // Launch the round over the tiles [tile0, tile0 + n_tiles) (several launches when one could overflow the s32 accumulators); the
 // last launch publishes the six integers into mapped slot `slot` of h_gemm and then `seq` into the slot's last word.
-int launch_gemm_round(sc_prover* p, const sck::RoundParams& rp, bool fold, unsigned long long tile0, unsigned long long n_tiles, uint32_t slot, uint32_t seq) {
+constexpr uint32_t GEMM_RMAIL_WORD = 480, GEMM_RERROR_WORD = 496;  // inside slot 0 of h_gemm (results use < 320 words, the flag the last one)
+
+int launch_gemm_round(sc_prover* p, const sck::RoundParams& rp, bool fold, unsigned long long tile0, unsigned long long n_tiles, uint32_t slot, uint32_t seq,
+                      bool wait_r = false) {
     gsum::Params G;
     memset(&G, 0, sizeof(G));
     G.rp = rp;
+    if (wait_r) {
+        G.r_mail = (const unsigned long long*)(p->d_gemm + GEMM_RMAIL_WORD);
+        G.r_bcast = p->d_gemm_totals + (size_t)9 * gsum::TOT_STRIDE;
+        G.r_seq = seq;
+        G.r_error = p->d_gemm + GEMM_RERROR_WORD;
+        const int khz = g_dev[p->device].khz;
+        static const double secs = getenv("SC_RES_TIMEOUT_S") ? atof(getenv("SC_RES_TIMEOUT_S")) : 10.0;
+        G.r_timeout = (long long)(secs * (khz > 0 ? khz : 1965000) * 1000.0);
+    }
     G.ymaps = p->d_ymaps;
     G.totals = p->d_gemm_totals;
     G.rp.host_out = p->d_gemm + (size_t)slot * gsum::OUT_SLOT_WORDS;
@@ -491,6 +507,59 @@ int launch_gemm_round(sc_prover* p, const sck::RoundParams& rp, bool fold, unsig
     return SC_OK;
 }
 
+// The challenge of a fold round that was launched ahead: eight {limb, sequence number} words, each ONE aligned 8-byte store
+void gemm_send_challenge(sc_prover* p, const uint64_t* r /* null: zeros (abandoned proof) */, uint32_t seq) {
+    uint64_t* m = (uint64_t*)(p->h_gemm + GEMM_RMAIL_WORD);
+    for (int k = 0; k < 4; k++) {
+        const uint64_t limb = r ? r[k] : 0;
+        __atomic_store_n(m + 2 * k, (uint64_t)(uint32_t)limb | ((uint64_t)seq << 32), __ATOMIC_RELAXED);
+        __atomic_store_n(m + 2 * k + 1, (limb >> 32) | ((uint64_t)seq << 32), __ATOMIC_RELAXED);
+    }
+    __sync_synchronize();
+}
+
+// An abandoned proof (error paths, reset, destroy): release a kernel that still waits for its challenge and let it drain
+void gemm_abort_prelaunch(sc_prover* p) {
+    if (!p->gemm_pre_round) return;
+    gemm_send_challenge(p, nullptr, p->gemm_pre_want);
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    p->gemm_pre_round = 0;
+}
+
+// Right after round p->round has been issued (p->cur names the buffer it writes): if the NEXT round is a contraction fold round
+// with a launch of its own, launch it now — it starts when this round's kernel ends, runs its prologue and stages its first table
+// tiles while the host is still finishing and hashing this round's message, and picks the challenge up from mapped memory.
+// Saves the launch latency, the prologue and the first TMA round trip of every large fold round (~8 us each).
+int gemm_prelaunch(sc_prover* p) {
+    static const bool off = getenv("SC_NO_PRELAUNCH") != nullptr;
+    if (off || !p->prelaunch_ok || p->comm || p->is_shard || (p->timing && p->want_timing) || p->gemm_pre_round) return SC_OK;
+    const uint32_t i2 = p->round + 1;
+    if (i2 < 2 || i2 > p->nv_local || (p->res_first && i2 >= p->res_first)) return SC_OK;
+    const unsigned long long n_pairs = (unsigned long long)1 << (p->nv_local - i2);
+    if (!gemm_round_ok(p, n_pairs, true)) return SC_OK;
+    sck::RoundParams rp;
+    memset(&rp, 0, sizeof(rp));
+    uint32_t** in = p->cur == 0 ? p->d_ptr0 : (p->cur == 1 ? p->d_ptrA : p->d_ptrB);
+    uint32_t** out = p->cur == 1 ? p->d_ptrB : p->d_ptrA;
+    rp.tab_in = (const uint32_t* const*)in;
+    rp.tab_out = out;
+    rp.prod_offsets = p->d_offsets; rp.prod_indices = p->d_indices; rp.prod_first = p->d_first; rp.coeffs = p->d_coeffs;
+    rp.prod_scaled = p->d_scaled;
+    rp.n_products = p->n_products; rp.n_tables = p->T; rp.defer_coeff = (p->n_products == 1) ? 1u : 0u;
+    rp.n_pairs = n_pairs;
+    rp.counter = p->d_counter;
+    rp.degree = p->d;
+    rp.write_fold = 1;
+    rp.tmaps = p->d_maps + (size_t)p->cur * p->T * sizeof(CUtensorMap);
+    const uint32_t want = ++p->gemm_seq;
+    int rc = launch_gemm_round(p, rp, true, 0, n_pairs / gsum::TILE, 0, want, true);
+    if (rc) return rc;
+    p->gemm_pre_round = i2;
+    p->gemm_pre_want = want;
+    return SC_OK;
+}
+
 // One protocol round on the device: (fold on r) + sums for all d+1 points.  Results land in d_evals / d_canon.
 int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
     const uint32_t i = p->round;  // already incremented: 1-based round being computed
@@ -501,6 +570,25 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
     int next = p->cur;
     if (fold) next = (p->cur == 1) ? 2 : 1;
     uint32_t** out = next == 1 ? p->d_ptrA : p->d_ptrB;
+    if (p->gemm_pre_round) {
+        if (p->gemm_pre_round != i || !fold) {  // (cannot happen inside run_rounds; a stale kernel must not outlive its proof)
+            gemm_abort_prelaunch(p);
+        } else {
+            // this round's kernel is already on the GPU (gemm_prelaunch): all that is left to do is to send the challenge
+            gemm_send_challenge(p, r, p->gemm_pre_want);
+            p->gemm_want = p->gemm_pre_want;
+            p->gemm_pre_round = 0;
+            p->direct_active = true;
+            p->raw_active = true;
+            p->alt_active = false;
+            p->gemm_active = true;
+            p->used_skip1 = false;
+            p->gemm_rounds++;
+            p->tc_rounds++;
+            p->cur = next;
+            return SC_OK;
+        }
+    }
     rp.tab_in = (const uint32_t* const*)in;
     rp.tab_out = out;
     rp.prod_offsets = p->d_offsets;
@@ -540,7 +628,8 @@ int run_round_device(sc_prover* p, const uint64_t* r /* null in round 1 */) {
         // host turns the six integers it receives into P(0..d) (host_finish_round)
         rp.write_fold = 1;
         rp.tmaps = fold ? p->d_maps + (size_t)p->cur * p->T * sizeof(CUtensorMap) : nullptr;
-        int rc = launch_gemm_round(p, rp, fold, 0, rp.n_pairs / gsum::TILE, 0, rp.seq);
+        p->gemm_want = ++p->gemm_seq;
+        int rc = launch_gemm_round(p, rp, fold, 0, rp.n_pairs / gsum::TILE, 0, p->gemm_want);
         if (rc) return rc;
         p->gemm_active = true;
         p->raw_active = true;
@@ -698,7 +787,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     const size_t oMaps = take((size_t)4 * T * sizeof(CUtensorMap));
     const size_t oScaled = take(n_products);
     const size_t oResB = take(RES_BCAST_BYTES), oResC = take(64 * sizeof(unsigned int));
-    const size_t oYmaps = take((size_t)T * sizeof(CUtensorMap)), oGemmTot = take((size_t)9 * gsum::TOT_STRIDE * sizeof(unsigned long long));
+    const size_t oYmaps = take((size_t)T * sizeof(CUtensorMap)), oGemmTot = take((size_t)9 * gsum::TOT_STRIDE * sizeof(unsigned long long) + 64);
     TRY_P(device_alloc((void**)&p->slabA, off, &p->slabA_bytes, device));
     uint8_t* base = (uint8_t*)p->slabA;
     for (uint32_t j = 0; j < T; j++) {
@@ -713,7 +802,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     TRY_P(cudaMemsetAsync(p->d_res_bcast, 0, RES_BCAST_BYTES, p->stream));  // a recycled slab may hold another handle's sequence numbers
     p->d_ymaps = base + oYmaps;
     p->d_gemm_totals = (unsigned long long*)(base + oGemmTot);
-    TRY_P(cudaMemsetAsync(p->d_gemm_totals, 0, (size_t)9 * gsum::TOT_STRIDE * sizeof(unsigned long long), p->stream));
+    TRY_P(cudaMemsetAsync(p->d_gemm_totals, 0, (size_t)9 * gsum::TOT_STRIDE * sizeof(unsigned long long) + 64, p->stream));  // + the 8 challenge words
     p->d_tail_evals = (uint32_t*)(base + oTe); p->d_tail_chal = (uint32_t*)(base + oTc); p->d_st = (b2::State*)(base + oSt);
     {
         // TMA descriptors (fold rounds with >= tc_min_pairs output pairs run on the TMA + tensor-core kernel)
@@ -1346,7 +1435,7 @@ int prove_round_issue(sc_prover* p, const uint64_t* r_or_null) {
         p->direct_active = true;
         if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));  // the round's work ran during the upload
         if (p->res_first && p->round + 1 == p->res_first) return resident_launch(p);
-        return SC_OK;  // nothing left to collect
+        return gemm_prelaunch(p);  // nothing left to collect; round 2 can start its prologue while the caller hashes round 1
     }
     if (p->comm) {
         rc = sharded_round(p, r_or_null);
@@ -1354,6 +1443,7 @@ int prove_round_issue(sc_prover* p, const uint64_t* r_or_null) {
         rc = run_round_device(p, r_or_null);
         p->out_evals = p->d_evals;
         p->out_canon = p->d_canon;
+        if (!rc) rc = gemm_prelaunch(p);  // the next large fold round right behind this one (whole-proof calls only)
     }
     if (rc) return rc;
     if (timed) CUDA_TRY(cudaEventRecord(p->ev[2 * (p->round - 1) + 1], p->stream));
@@ -1386,7 +1476,7 @@ int prove_round_collect(sc_prover* p, const uint64_t* r_or_null, bool sync_out) 
         // the last block wrote the message into mapped pinned memory and then the flag: spin instead of copy + sync
         sc_prover* w = (p->comm && p->wait_on) ? p->wait_on : p;
         volatile uint32_t* flag = w->gemm_active ? w->h_gemm + gsum::OUT_SLOT_WORDS - 1 : w->h_result + (size_t)(p->d + 1) * 16;
-        const uint32_t want = w->seq;
+        const uint32_t want = w->gemm_active ? w->gemm_want : w->seq;
         SpinWait sw;
         while (*flag != want) {
             sw.pause();
@@ -1397,6 +1487,10 @@ int prove_round_collect(sc_prover* p, const uint64_t* r_or_null, bool sync_out) 
             }
         }
         __sync_synchronize();
+        if (w->gemm_active && w->h_gemm[GEMM_RERROR_WORD]) {
+            w->h_gemm[GEMM_RERROR_WORD] = 0;
+            return fail(SC_ERR_CUDA, "a fold round launched ahead of its challenge gave up waiting for it");
+        }
         if (w->raw_active) {
             host_finish_round(p, w, r_or_null);
         } else if (w != p) {
@@ -1528,8 +1622,11 @@ int run_rounds(sc_prover* p, b2::State* st, uint64_t* evals_out, uint64_t* chall
     const uint32_t tail_first = tail_first_round(p);
     p->timing = true;
     p->res_first = resident_first_round(p);
+    p->prelaunch_ok = true;
     auto bail = [&](int rc) {
         p->timing = false;
+        p->prelaunch_ok = false;
+        gemm_abort_prelaunch(p);
         resident_abort(p);
         if (p->sub) { resident_abort(p->sub); p->sub->res_first = 0; }
         p->res_first = 0;
@@ -1553,6 +1650,8 @@ int run_rounds(sc_prover* p, b2::State* st, uint64_t* evals_out, uint64_t* chall
     p->res_first = 0;
     if (p->sub) p->sub->res_first = 0;
     p->timing = false;
+    p->prelaunch_ok = false;
+    gemm_abort_prelaunch(p);  // (none is pending after a complete proof)
     if (p->want_timing) {
         cudaStreamSynchronize(p->stream);
         for (uint32_t i = 0; i < nv; i++) cudaEventElapsedTime(&p->round_ms[i], p->ev[2 * i], p->ev[2 * i + 1]);
@@ -1636,6 +1735,7 @@ void sc_prover_destroy(sc_prover* p) {
     if (!p) return;
     if (!p->group.empty() || p->workers) { multi_destroy(p); return; }
     cudaSetDevice(p->device);
+    gemm_abort_prelaunch(p);
     resident_abort(p);
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->sub) { p->sub->stream = p->sub->own_stream; sc_prover_destroy(p->sub); cudaSetDevice(p->device); }
@@ -1660,6 +1760,7 @@ void sc_prover_destroy(sc_prover* p) {
 int sc_prover_reset(sc_prover* p) {
     NEED_HANDLE(p);
     if (!p->group.empty()) return multi_reset(p);
+    gemm_abort_prelaunch(p);
     p->round = 0;
     p->cur = 0;
     p->randomness.clear();

@@ -408,6 +408,41 @@ def test_contraction_rounds_special_values_and_edge_challenges(orc, monkeypatch,
     assert st.gemm_round_count() == 4   # rounds 1..4 of nv=11 (1024 .. 128 pairs)
 
 
+@pytest.mark.parametrize("nv,n_products,m", [(12, 1, 3), (13, 2, 3), (12, 1, 4)])
+def test_fold_rounds_launched_ahead_of_their_challenge(orc, monkeypatch, nv, n_products, m):
+    """Inside a whole-proof call the next large fold round is launched right behind the current one and receives its challenge
+    through mapped memory (gemm_prelaunch).  Same proof as the oracle's, as with SC_NO_PRELAUNCH=1, as through caller-driven rounds
+    (which never launch ahead), and the same number of launches; a second proof on the handle after reset."""
+    import ctypes as C
+    monkeypatch.setenv("SC_TC_MIN_PAIRS", "128")
+    monkeypatch.setenv("SC_RES_MAX_PAIRS", "64")
+    tables, products = random_instance(9900 + nv + m, nv, n_products, (m, m + 1), False)
+    poly, opoly = both_polys(orc, nv, tables, products)
+    want = orc.ml_prove(opoly)[0]
+    st = sc.IPForMLSumcheck.prover_init(poly)
+    ev = np.zeros((nv, m + 1, 4), dtype=np.uint64)
+    for rep in range(2):
+        st.reset()
+        ev[:] = 0
+        st.prove_into(sc.Blake2b512Rng.setup(), ev)
+        assert np.array_equal(ev, want)
+        assert st.gemm_round_count() == nv - 7
+    launches = st.launch_count()
+    # caller-driven rounds on the same handle
+    st.reset()
+    ost = orc.Prover(opoly)
+    v = None
+    for i in range(nv):
+        msg = sc.IPForMLSumcheck.prove_round(st, v)
+        assert np.array_equal(msg.evaluations, ost.prove_round(None if v is None else v.randomness))
+        v = sc.VerifierMsg(limbs(7 + i))
+    monkeypatch.setenv("SC_NO_PRELAUNCH", "1")   # read once per process: only effective if nothing launched ahead before
+    st2 = sc.IPForMLSumcheck.prover_init(poly)
+    ev2 = np.zeros_like(ev)
+    st2.prove_into(sc.Blake2b512Rng.setup(), ev2)
+    assert np.array_equal(ev2, want) and st2.launch_count() == launches
+
+
 def test_reset_reproves_identically(orc):
     nv = 10
     tabs = [orc.synth_table(1 << nv, 900 + j) for j in range(3)]
