@@ -419,6 +419,8 @@ cudaError_t launch_round1_tma(sc_prover* p, const sck::RoundParams& rp) {
 }
 
 void set_exchange_params(sc_prover* p, sck::RoundParams& rp);  // capi_multi.inc
+bool comm_fused_exchange_ok(const sc_prover* p);  // the sharded rounds of this handle run the fused peer-memory exchange
+int comm_device_share(const sc_prover* p);        // ranks of the group that share this rank's device
 uint32_t set_exchange_params_resident(sc_prover* p, sck::RoundParams& rp, uint32_t n_rounds);
 bool comm_failed(const sc_prover* p);
 void comm_clear_error(sc_prover* p);
@@ -533,11 +535,21 @@ void gemm_abort_prelaunch(sc_prover* p) {
 // Saves the launch latency, the prologue and the first TMA round trip of every large fold round (~8 us each).
 int gemm_prelaunch(sc_prover* p) {
     static const bool off = getenv("SC_NO_PRELAUNCH") != nullptr;
-    if (off || !p->prelaunch_ok || p->comm || p->is_shard || (p->timing && p->want_timing) || p->gemm_pre_round) return SC_OK;
+    if (off || !p->prelaunch_ok || (p->timing && p->want_timing) || p->gemm_pre_round) return SC_OK;
     const uint32_t i2 = p->round + 1;
     if (i2 < 2 || i2 > p->nv_local || (p->res_first && i2 >= p->res_first)) return SC_OK;
     const unsigned long long n_pairs = (unsigned long long)1 << (p->nv_local - i2);
-    if (!gemm_round_ok(p, n_pairs, true)) return SC_OK;
+    if (p->comm) {
+        // a shard: only sharded rounds with the fused exchange, and only when this rank has its GPU to itself — a kernel that
+        // waits for its challenge holds every SM, and a rank sharing the device could then never finish the round it waits for
+        if (!comm_fused_exchange_ok(p) || comm_device_share(p) > 1 || i2 >= p->switch_round) return SC_OK;
+        p->exchange = true;
+        const bool ok = gemm_round_ok(p, n_pairs, true);
+        p->exchange = false;
+        if (!ok) return SC_OK;
+    } else if (p->is_shard || !gemm_round_ok(p, n_pairs, true)) {
+        return SC_OK;
+    }
     sck::RoundParams rp;
     memset(&rp, 0, sizeof(rp));
     uint32_t** in = p->cur == 0 ? p->d_ptr0 : (p->cur == 1 ? p->d_ptrA : p->d_ptrB);
@@ -552,6 +564,7 @@ int gemm_prelaunch(sc_prover* p) {
     rp.degree = p->d;
     rp.write_fold = 1;
     rp.tmaps = p->d_maps + (size_t)p->cur * p->T * sizeof(CUtensorMap);
+    if (p->comm) set_exchange_params(p, rp);  // mailbox slot and sequence number of that round (handed out in launch order on every rank)
     const uint32_t want = ++p->gemm_seq;
     int rc = launch_gemm_round(p, rp, true, 0, n_pairs / gsum::TILE, 0, want, true);
     if (rc) return rc;
@@ -1439,6 +1452,7 @@ int prove_round_issue(sc_prover* p, const uint64_t* r_or_null) {
     }
     if (p->comm) {
         rc = sharded_round(p, r_or_null);
+        if (!rc) rc = gemm_prelaunch(p);
     } else {
         rc = run_round_device(p, r_or_null);
         p->out_evals = p->d_evals;
