@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "gemm_sum.cuh"
 
@@ -25,6 +26,8 @@ constexpr int G1 = SC_GEMM_G1, GF = SC_GEMM_GF, GF4 = SC_GEMM_GF4;
 template <int TAG, class K>
 static cudaError_t prepare(K kernel, size_t smem) {
     static bool ready_dev[64] = {};
+    static std::mutex mu;  // handles may live on different host threads (one per rank of an in-process group)
+    std::lock_guard<std::mutex> lk(mu);
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;

@@ -75,6 +75,14 @@ struct SpinWait {
     inline bool check_now() const { return (n & 0xffff) == 0; }  // time to ask the driver whether the kernel died
 };
 
+// Nsight Compute makes every launch synchronous and replays kernels: a kernel that waits for words the host writes AFTER the launch call
+// returns (the resident rounds, a fold round launched ahead of its challenge) can never finish under it.  ncu marks the profiled process
+// with these variables; with them set the library runs one self-contained launch per round, so `ncu python bench.py` just works.
+bool profiler_attached() {
+    static const bool on = getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr || getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") != nullptr;
+    return on;
+}
+
 struct DeviceInfo {
     bool ready = false;
     int sms = 0;
@@ -534,7 +542,7 @@ void gemm_abort_prelaunch(sc_prover* p) {
 // tiles while the host is still finishing and hashing this round's message, and picks the challenge up from mapped memory.
 // Saves the launch latency, the prologue and the first TMA round trip of every large fold round (~8 us each).
 int gemm_prelaunch(sc_prover* p) {
-    static const bool off = getenv("SC_NO_PRELAUNCH") != nullptr;
+    static const bool off = getenv("SC_NO_PRELAUNCH") != nullptr || profiler_attached();
     if (off || !p->prelaunch_ok || (p->timing && p->want_timing) || p->gemm_pre_round) return SC_OK;
     const uint32_t i2 = p->round + 1;
     if (i2 < 2 || i2 > p->nv_local || (p->res_first && i2 >= p->res_first)) return SC_OK;
@@ -923,7 +931,7 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
     memset(p->h_gemm, 0, hGemm);
     {
         const char* env = getenv("SC_RES_MAX_PAIRS");
-        p->res_max_pairs = getenv("SC_NO_RESIDENT") ? 0 : (env ? strtoull(env, nullptr, 10) : RES_MAX_PAIRS_DEFAULT);
+        p->res_max_pairs = (getenv("SC_NO_RESIDENT") || profiler_attached()) ? 0 : (env ? strtoull(env, nullptr, 10) : RES_MAX_PAIRS_DEFAULT);
     }
     p->host_post = !getenv("SC_TAIL") && !getenv("SC_NO_HOST_POST");
     p->h_prev.assign((size_t)(d + 1) * 4, 0);
