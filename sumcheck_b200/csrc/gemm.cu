@@ -63,12 +63,12 @@ static cudaError_t launch_r1(const Params& P, int sms, cudaStream_t stream) {
     gemm_round1_kernel<G, MM><<<grid_for(P.items, G, sms), G * 128 + 64, smem, stream>>>(P);
     return cudaGetLastError();
 }
-template <int TAG, int G, int MM>
+template <int TAG, int G, int MM, bool PRE>
 static cudaError_t launch_f(const Params& P, int sms, cudaStream_t stream) {
     const size_t smem = FoldSmem<G, MM>::BYTES;
-    cudaError_t e = prepare<TAG>(gemm_fold_kernel<G, MM>, smem);
+    cudaError_t e = prepare<TAG>(gemm_fold_kernel<G, MM, PRE>, smem);
     if (e != cudaSuccess) return e;
-    gemm_fold_kernel<G, MM><<<grid_for(P.items, G, sms), G * 128 + 96, smem, stream>>>(P);
+    gemm_fold_kernel<G, MM, PRE><<<grid_for(P.items, G, sms), G * 128 + 96, smem, stream>>>(P);
     return cudaGetLastError();
 }
 
@@ -76,7 +76,8 @@ cudaError_t launch_round1(const Params& P, int mm, int sms, cudaStream_t stream)
     return mm == 4 ? launch_r1<3, G1, 4>(P, sms, stream) : launch_r1<1, G1, 3>(P, sms, stream);
 }
 cudaError_t launch_fold(const Params& P, int mm, int sms, cudaStream_t stream) {
-    return mm == 4 ? launch_f<4, GF4, 4>(P, sms, stream) : launch_f<2, GF, 3>(P, sms, stream);
+    if (P.r_mail) return mm == 4 ? launch_f<6, GF4, 4, true>(P, sms, stream) : launch_f<5, GF, 3, true>(P, sms, stream);
+    return mm == 4 ? launch_f<4, GF4, 4, false>(P, sms, stream) : launch_f<2, GF, 3, false>(P, sms, stream);
 }
 
 }  // namespace gsum

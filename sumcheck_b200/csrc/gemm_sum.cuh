@@ -642,7 +642,10 @@ struct FoldSmem {
 // Tensor memory: 2 N columns of contraction accumulators, then NACC fix_variables accumulators of 64 columns per group — MM = 3: three
 // groups x two (alternating), MM = 4: two groups x one (the 384 contraction columns leave room for two; a group's compute per table
 // tile is several times the latency of its MMAs, so one accumulator per group does not starve it).  512 columns either way.
-template <int G, int MM>
+// PRE: the build for rounds launched ahead of their challenge.  A separate instantiation, because the mere presence of the polling loop
+// in the prologue made ptxas schedule the main loop ~3 % slower (measured A/B on one box: round 2 of nv = 24 0.390 vs 0.403 ms) — the
+// ordinary build must not carry it.
+template <int G, int MM, bool PRE = false>
 __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params P) {
     using L = FoldSmem<G, MM>;
     using S_ = Shape<MM>;
@@ -684,7 +687,7 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
     const uint32_t tmem = s_tmem;
     if (warp < 2) {   // ... while warps 0 and 1 expand the challenge into the constants matrix, which only the first
         Fr r;         // fix_variables MMA waits for (named barrier 1: these two warps arrive, the MMA-issuing warp syncs)
-        if (P.r_mail) {  // launched ahead of the challenge: wait for the host to send it
+        if (PRE) {  // launched ahead of the challenge: wait for the host to send it
             __shared__ uint32_t s_r[8];
             if (tid < 8) {
                 unsigned long long w;

@@ -547,6 +547,11 @@ int gemm_prelaunch(sc_prover* p) {
     const uint32_t i2 = p->round + 1;
     if (i2 < 2 || i2 > p->nv_local || (p->res_first && i2 >= p->res_first)) return SC_OK;
     const unsigned long long n_pairs = (unsigned long long)1 << (p->nv_local - i2);
+    {   // the build that can wait for its challenge runs its main loop ~3 % slower (gemm_sum.cuh): only worth it where that is less than
+        // the ~8 us a launch ahead saves, i.e. for rounds of up to 2^21 pairs x 3 tables
+        static const unsigned long long cap = getenv("SC_PRELAUNCH_MAX_PAIRS") ? strtoull(getenv("SC_PRELAUNCH_MAX_PAIRS"), nullptr, 10) : (3ull << 21);
+        if (n_pairs * p->h_nnz > cap) return SC_OK;
+    }
     if (p->comm) {
         // a shard: only sharded rounds with the fused exchange, and only when this rank has its GPU to itself — a kernel that
         // waits for its challenge holds every SM, and a rank sharing the device could then never finish the round it waits for
