@@ -79,7 +79,8 @@ struct SpinWait {
 // returns (the resident rounds, a fold round launched ahead of its challenge) can never finish under it.  ncu marks the profiled process
 // with these variables; with them set the library runs one self-contained launch per round, so `ncu python bench.py` just works.
 bool profiler_attached() {
-    static const bool on = getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr || getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") != nullptr;
+    static const bool on = getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr || getenv("NV_NSIGHT_INJECTION_TRANSPORT_TYPE") != nullptr ||
+                           (getenv("CUDA_LAUNCH_BLOCKING") && atoi(getenv("CUDA_LAUNCH_BLOCKING")) != 0);  // (the same holds for blocking launches)
     return on;
 }
 
