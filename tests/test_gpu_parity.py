@@ -443,6 +443,45 @@ def test_fold_rounds_launched_ahead_of_their_challenge(orc, monkeypatch, nv, n_p
     assert np.array_equal(ev2, want) and st2.launch_count() == launches
 
 
+@pytest.mark.parametrize("n_products,m", [(1, 3), (1, 4), (2, 3)])
+def test_contraction_rounds_on_borrowed_device_tables(orc, monkeypatch, n_products, m):
+    """sc_prover_create_device: the caller's tables already live in HBM and are borrowed, never written.  One product: the
+    contraction kernels read them through descriptors built on the caller's pointers; several products: nothing can be
+    pre-scaled in place (the tables are not ours), so the rounds fall back — both must agree with the oracle, twice (reset)."""
+    import ctypes as C
+    import torch
+    monkeypatch.setenv("SC_TC_MIN_PAIRS", "128")
+    monkeypatch.setenv("SC_RES_MAX_PAIRS", "64")
+    nv = 11
+    tables, products = random_instance(12000 + n_products + 10 * m, nv, n_products, (m, m + 1), False)
+    poly, opoly = both_polys(orc, nv, tables, products)
+    want = orc.ml_prove(opoly)[0]
+    tabs = [np.ascontiguousarray(t) for t in opoly.tables]
+    dev = [torch.from_numpy(t.view(np.int64)).cuda() for t in tabs]
+    before = [d.clone() for d in dev]
+    ptrs = (C.c_void_p * len(dev))(*[d.data_ptr() for d in dev])
+    coeffs = np.ascontiguousarray(np.stack([limbs(c) for c, _ in products]))
+    offsets = np.array([0] + list(np.cumsum([len(ix) for _, ix in products])), dtype=np.uint32)
+    indices = np.array([j for _, ix in products for j in ix], dtype=np.uint32)
+    h = C.c_void_p()
+    L = sc.lib()
+    assert L.sc_prover_create_device(C.byref(h), nv, len(dev), ptrs, n_products, coeffs.ctypes.data_as(sc.capi.U64P),
+                                     offsets.ctypes.data_as(sc.capi.U32P), indices.ctypes.data_as(sc.capi.U32P), 0) == 0
+    try:
+        for rep in range(2):
+            assert L.sc_prover_reset(h) == 0
+            ev = np.zeros((nv, m + 1, 4), dtype=np.uint64)
+            rng = sc.Blake2b512Rng.setup()
+            assert L.sc_ml_prove(h, C.byref(rng.state), ev.ctypes.data_as(sc.capi.U64P), None) == 0
+            assert np.array_equal(ev, want)
+        assert (L.sc_prover_gemm_round_count(h) == nv - 7) == (n_products == 1)
+        torch.cuda.synchronize()
+        for d, b in zip(dev, before):
+            assert torch.equal(d, b)   # borrowed tables are never written
+    finally:
+        L.sc_prover_destroy(h)
+
+
 def test_reset_reproves_identically(orc):
     nv = 10
     tabs = [orc.synth_table(1 << nv, 900 + j) for j in range(3)]
