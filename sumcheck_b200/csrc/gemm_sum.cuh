@@ -99,15 +99,22 @@ __device__ __forceinline__ uint64_t mn_desc(uint32_t smem_addr, uint32_t sbo_byt
 //   MM = 4: the three plain products s0, s1, ss of tables 2 and 3, three blocks of 64 bytes (three SWIZZLE_64B arrays 8 KiB apart,
 //           N = 192 through the descriptor's leading byte offset) — again no modular arithmetic anywhere in the hot loop.
 // D = X^T Y has 3 x NBY block pairs; block pair (i, j) yields sum_b X_i * Y_j as an integer of OUT_LIMBS limbs.
+//   MM = 2 (GKR phases, degree-2 lists): X = the first table's pair [a0 | b0], Y = the second table's pair — NO per-pair
+//           multiplication at all: in round 1 both operands are the tiles as TMA lands them, a fold round only reads the folded pairs
+//           out of tensor memory and writes them back as operands.  One M = 64 accumulator (XQ's place), two blocks of 32 bytes a side.
 template <int MM>
 struct Shape;
 template <>
+struct Shape<2> {
+    static constexpr uint32_t NBX = 2, BX = 32, NBY = 2, BY = 32, N = 64, NB = 4, DIAG = 63, ES = 64, OUT_LIMBS = 18, Y_BYTES = 8192;
+};
+template <>
 struct Shape<3> {
-    static constexpr uint32_t NBY = 2, BY = 32, N = 64, NB = 6, DIAG = 95, ES = 96, OUT_LIMBS = 26, Y_BYTES = 8192;
+    static constexpr uint32_t NBX = 3, BX = 64, NBY = 2, BY = 32, N = 64, NB = 6, DIAG = 95, ES = 96, OUT_LIMBS = 26, Y_BYTES = 8192;
 };
 template <>
 struct Shape<4> {
-    static constexpr uint32_t NBY = 3, BY = 64, N = 192, NB = 9, DIAG = 127, ES = 128, OUT_LIMBS = 34, Y_BYTES = 24576;
+    static constexpr uint32_t NBX = 3, BX = 64, NBY = 3, BY = 64, N = 192, NB = 9, DIAG = 127, ES = 128, OUT_LIMBS = 34, Y_BYTES = 24576;
 };
 // c_format S32 @4, a/b U8, a_major = b_major = MN @15/@16, N>>3 @17, M>>4 @24
 __host__ __device__ constexpr uint32_t idesc_u8_mn(uint32_t M, uint32_t N) {
@@ -323,8 +330,12 @@ __device__ __forceinline__ void issue_contraction(uint32_t xa_smem, uint32_t xq_
 #pragma unroll
     for (uint32_t ks = 0; ks < 4; ks++) {
         const uint64_t b = mn_desc(y_smem + ks * 2048u, 512, 4, 8192);
-        umma(tmem_d, mn_desc(xa_smem + ks * 4096u, 1024, 2), b, I128, accumulate | ks);
-        umma(tmem_d + N, mn_desc(xq_smem + ks * 2048u, 512, 4), b, I64, accumulate | ks);
+        if (MM == 2) {  // one 64-byte X operand (the first table's pair), one accumulator
+            umma(tmem_d, mn_desc(xq_smem + ks * 2048u, 512, 4), b, I64, accumulate | ks);
+        } else {
+            umma(tmem_d, mn_desc(xa_smem + ks * 4096u, 1024, 2), b, I128, accumulate | ks);
+            umma(tmem_d + N, mn_desc(xq_smem + ks * 2048u, 512, 4), b, I64, accumulate | ks);
+        }
     }
 }
 
@@ -340,6 +351,7 @@ __device__ __forceinline__ void epilogue(const Params& P, uint32_t tmem_d, bool 
                                          long long t_start = 0) {
     using S_ = Shape<MM>;
     constexpr uint32_t NB = S_::NB, ES = S_::ES, DIAG = S_::DIAG, OUT_LIMBS = S_::OUT_LIMBS, N = S_::N, BY = S_::BY, NBY = S_::NBY;
+    constexpr uint32_t PARTS = (MM == 2 ? 1 : 2) * N / 32;  // MM = 2 has the M = 64 accumulator only (at column 0)
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     prof_mark(P.prof, 13, t_start);  // main loop done
     for (uint32_t i = tid; i < 2 * NB * ES; i += blockDim.x) s_E[i] = 0;
@@ -349,13 +361,14 @@ __device__ __forceinline__ void epilogue(const Params& P, uint32_t tmem_d, bool 
         const uint32_t lane_addr = tmem_d + ((warp * 32u) << 16);
         uint32_t S[32];
 #pragma unroll 1
-        for (uint32_t part = 0; part < 2 * N / 32; part++) {  // 32 columns at a time: D1 first, then D2
-            const bool second = part >= N / 32;
+        for (uint32_t part = 0; part < PARTS; part++) {  // 32 columns at a time: D1 first, then D2
+            const bool second = MM == 2 || part >= N / 32;
             tcf::tmem_ld32(lane_addr + part * 32u, S);  // (whole warp: .sync.aligned)
             tcf::tmem_ld_wait();
-            if (second && lane >= 16) continue;  // D2 (M = 64) lives in lanes 0..15 of every 32-lane quadrant
-            const uint32_t i = second ? 2u : (tid >> 6), u = second ? (warp * 16u + lane) : (tid & 63u);
-            const uint32_t c0 = (second ? part - N / 32 : part) * 32u, j = c0 / BY, v0 = c0 % BY;
+            if (second && lane >= 16) continue;  // an M = 64 accumulator lives in lanes 0..15 of every 32-lane quadrant
+            const uint32_t row = warp * 16u + lane;  // (of an M = 64 accumulator)
+            const uint32_t i = MM == 2 ? (row >> 5) : (second ? 2u : (tid >> 6)), u = MM == 2 ? (row & 31u) : (second ? row : (tid & 63u));
+            const uint32_t c0 = ((second && MM != 2) ? part - N / 32 : part) * 32u, j = c0 / BY, v0 = c0 % BY;
             uint32_t* lo = s_E + (NBY * i + j) * ES + u + v0;
             uint32_t* hi = lo + NB * ES;
 #pragma unroll
@@ -621,6 +634,74 @@ __global__ void __launch_bounds__(G * 128 + 64, 1) gemm_round1_kernel(const Para
     if (warp == 0) tcf::tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// ================================================================================================ round 1 of two-table products
+// Both operands are the tables' tiles as TMA lands them (64-byte rows = one pair, SWIZZLE_64B): the kernel is a TMA warp, an MMA warp
+// and four warps that only run the epilogue — not one multiplication on the CUDA cores.  Items (tile, product) are dealt to the CTAs
+// round-robin; a ring of RAW_STAGES (X, Y) tile pairs.
+constexpr uint32_t RAW_STAGES = 8, RAW_STAGE_BYTES = 16384, RAW_THREADS = 192;
+constexpr size_t RAW_SMEM = (size_t)RAW_STAGES * RAW_STAGE_BYTES;
+
+template <int MM = 2>  // (a template only so that the header can be included by several translation units)
+__global__ void __launch_bounds__(RAW_THREADS, 1) gemm_round1_raw_kernel(const Params P) {
+    static_assert(MM == 2, "two-table products");
+    using S_ = Shape<2>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full[RAW_STAGES], empty[RAW_STAGES], done;
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint32_t s_E[2 * S_::NB * S_::ES];
+    __shared__ bool s_last;
+    __shared__ CsrCache s_csr;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const sck::RoundParams& p = P.rp;
+    load_csr<2>(s_csr, p, false);
+    if (tid == 0) {
+        if (tcf::smem_u32(smem) & 1023u) __trap();
+        for (uint32_t s = 0; s < RAW_STAGES; s++) {
+            tcf::mbar_init(&full[s], 1);
+            tcf::mbar_init(&empty[s], 1);
+        }
+        tcf::mbar_init(&done, 1);
+        tcf::fence_mbar_init();
+    }
+    if (warp == 0) tcf::tmem_alloc(&s_tmem, 64);
+    tcf::tc_fence_before();
+    __syncthreads();
+    tcf::tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    const uint32_t n_items = blockIdx.x < P.items ? (P.items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    const bool one_product = p.n_products == 1;
+    if (warp == 4) {
+        if (lane == 0)
+            for (uint32_t n = 0; n < n_items; n++) {
+                const uint32_t slot = n % RAW_STAGES, w = blockIdx.x + n * gridDim.x;
+                const uint32_t k = one_product ? 0u : w % p.n_products, tile = p.tile_base + (one_product ? w : w / p.n_products);
+                if (n >= RAW_STAGES) tcf::mbar_wait(&empty[slot], ((n / RAW_STAGES) - 1u) & 1u);
+                uint8_t* dst = smem + (size_t)slot * RAW_STAGE_BYTES;
+                tcf::mbar_expect_tx(&full[slot], RAW_STAGE_BYTES);
+                tcf::tma_load_tile(dst, (const uint8_t*)P.ymaps + (size_t)s_csr.idx[2 * k] * 128, &full[slot], tile * TILE);
+                tcf::tma_load_tile(dst + 8192, (const uint8_t*)P.ymaps + (size_t)s_csr.idx[2 * k + 1] * 128, &full[slot], tile * TILE);
+            }
+    } else if (warp == 5) {
+        if (lane == 0 && n_items) {
+            for (uint32_t n = 0; n < n_items; n++) {
+                const uint32_t slot = n % RAW_STAGES, sb = tcf::smem_u32(smem + (size_t)slot * RAW_STAGE_BYTES);
+                tcf::mbar_wait(&full[slot], (n / RAW_STAGES) & 1u);
+                tcf::tc_fence_after();
+                issue_contraction<2>(0, sb, sb + 8192, tmem, n ? 1u : 0u);
+                tcf::umma_commit(&empty[slot]);
+            }
+            tcf::umma_commit(&done);
+            tcf::mbar_wait(&done, 0);
+        }
+    }
+    __syncwarp();
+    tcf::tc_fence_before();
+    __syncthreads();
+    epilogue<2>(P, tmem, n_items > 0, s_E, &s_last, reinterpret_cast<uint32_t*>(smem));
+    __syncthreads();
+    if (warp == 0) tcf::tmem_dealloc(tmem, 64);
+}
+
 // ================================================================================================ fold rounds, degree 3
 // Every table tile (128 rows x 128 bytes = old[4b..4b+3]) goes HBM -> shared memory by TMA into a ring shared by the groups
 // (warp W_TMA); warp W_FOLD issues the fix_variables MMAs (tc_fold.cuh) into the owning group's accumulator (two per group,
@@ -651,7 +732,7 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
     using S_ = Shape<MM>;
     constexpr uint32_t R = L::RING_SLOTS;
     constexpr uint32_t W_TMA = G * 4, W_FOLD = G * 4 + 1, W_SUM = G * 4 + 2;
-    constexpr uint32_t NACC = MM == 3 ? 2 : 1, ACC0 = 2 * S_::N;
+    constexpr uint32_t NACC = MM == 4 ? 1 : 2, ACC0 = 2 * S_::N;
     static_assert(ACC0 + G * NACC * 64 <= 512, "tensor memory");
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t slot_full[R], slot_empty[R], acc_full[G][2], acc_empty[G][2], x_full[G], x_empty[G];
@@ -759,7 +840,22 @@ __global__ void __launch_bounds__(G * 128 + 96, 1) gemm_fold_kernel(const Params
                     fr::store(dst, v0);
                     fr::store(dst + 8, v1);
                 }
-                if (j == 0 || (MM == 4 && j == 2)) {
+                if (MM == 2) {  // no products: the folded pair of table 0 is the X operand, that of table 1 the Y operand
+                    uint32_t y[16];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        y[i] = v0.l[i];
+                        y[8 + i] = v1.l[i];
+                    }
+                    if (j == 0) {
+                        t_x.start(pf);
+                        if (n > 0) tcf::mbar_wait(&x_empty[g], (n - 1) & 1u);
+                        t_x.stop(pf);
+                        sts_sw64(base + L::XQ, t, y);
+                    } else {
+                        sts_sw64(base + L::Y, t, y);
+                    }
+                } else if (j == 0 || (MM == 4 && j == 2)) {
                     e0 = v0;
                     o0 = v1;
                 } else if (j == 1) {

@@ -443,8 +443,10 @@ int multi_table(const sc_prover* P, uint32_t j, uint64_t* out, uint64_t cap_elem
 inline const sc_prover* lead(const sc_prover* p) { return (p && !p->group.empty()) ? p->group[0] : p; }
 
 // ---- tensor-core contraction rounds (gemm_sum.cuh) --------------------------------------------------------------------------------
-inline uint32_t gemm_limbs(const sc_prover* p) { return p->gemm_m == 4 ? gsum::Shape<4>::OUT_LIMBS : gsum::Shape<3>::OUT_LIMBS; }
-inline uint32_t gemm_nb(const sc_prover* p) { return p->gemm_m == 4 ? gsum::Shape<4>::NB : gsum::Shape<3>::NB; }
+inline uint32_t gemm_limbs(const sc_prover* p) {
+    return p->gemm_m == 4 ? gsum::Shape<4>::OUT_LIMBS : (p->gemm_m == 2 ? gsum::Shape<2>::OUT_LIMBS : gsum::Shape<3>::OUT_LIMBS);
+}
+inline uint32_t gemm_nb(const sc_prover* p) { return p->gemm_m == 4 ? gsum::Shape<4>::NB : (p->gemm_m == 2 ? gsum::Shape<2>::NB : gsum::Shape<3>::NB); }
 
 // May this round (n_pairs output pairs; fold = rounds >= 2) run on the contraction kernels?
 bool gemm_round_ok(const sc_prover* p, unsigned long long n_pairs, bool fold) {
@@ -897,9 +899,9 @@ int create_common(sc_prover** out, uint32_t nv, uint32_t T, const uint64_t* cons
         }
     }
     {
-        // Tensor-core contraction rounds (gemm_sum.cuh): every product has exactly three (d = 3) or exactly four (d = 4)
+        // Tensor-core contraction rounds (gemm_sum.cuh): every product has exactly two (d = 2), three (d = 3) or four (d = 4)
         // multiplicands; with several products every coefficient must already live in a table (checked per round: gemm_round_ok)
-        bool shape = (d == 3 || d == 4) && !getenv("SC_NO_GEMM") && !getenv("SC_NO_TC") && !(d == 4 && getenv("SC_NO_GEMM4"));
+        bool shape = (d >= 2 && d <= 4) && !getenv("SC_NO_GEMM") && !getenv("SC_NO_TC") && !(d == 4 && getenv("SC_NO_GEMM4")) && !(d == 2 && getenv("SC_NO_GEMM2"));
         for (uint32_t k = 0; k < n_products && shape; k++) shape = offsets[k + 1] - offsets[k] == d;
         p->gemm_shape = shape;
         p->gemm_m = shape ? d : 0;
@@ -1141,7 +1143,7 @@ void host_finish_round(sc_prover* p, sc_prover* w, const uint64_t* r) {
     const uint32_t d = p->d, ns = w->raw_npts;
     hfr::F sums[8], out[8], coeff;
     if (w->gemm_active) {  // the big integers from the contraction kernels (six at degree 3, nine at degree 4) -> P(0..d)
-        hfr::gemm_finish(w->h_gemm, gemm_limbs(p), 2, p->gemm_m - 2, d, out);
+        hfr::gemm_finish(w->h_gemm, gemm_limbs(p), p->gemm_m == 2 ? 1 : 2, p->gemm_m == 2 ? 1 : p->gemm_m - 2, d, out);
         if (p->n_products == 1) {
             memcpy(&coeff, p->h_coeffs.data(), 32);
             for (uint32_t t = 0; t <= d; t++) out[t] = hfr::mul(out[t], coeff);

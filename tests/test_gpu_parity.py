@@ -352,6 +352,11 @@ def test_tensor_core_fold_special_values_and_edge_challenges(orc, monkeypatch):
     (13, 1, False, None, 4),
     (12, 4, False, None, 4),    # the shape of BASELINE config 4: four products of four fresh tables
     (13, 2, False, 5, 4),
+    (8, 1, False, None, 2),     # products of TWO tables (GKR phases): no per-pair multiplication, round 1 is TMA + MMA only
+    (12, 1, False, None, 2),
+    (11, 1, True, None, 2),     # the same table twice
+    (13, 3, False, None, 2),
+    (13, 2, False, 3, 2),
 ])
 def test_contraction_rounds(orc, monkeypatch, nv, n_products, shared, max_tiles, m):
     """Products of three (or four) tables on the tensor-core contraction kernels (csrc/gemm_sum.cuh): plain products per pair, the
@@ -382,7 +387,7 @@ def test_contraction_rounds(orc, monkeypatch, nv, n_products, shared, max_tiles,
     assert np.array_equal(ev2, ev)
 
 
-@pytest.mark.parametrize("m", [3, 4])
+@pytest.mark.parametrize("m", [2, 3, 4])
 def test_contraction_rounds_special_values_and_edge_challenges(orc, monkeypatch, m):
     """0 / 1 / p-1 / all-0xff-byte tables and the challenges 0, 1, p-1 through the interactive API (sc_prove_round), folded tables
     compared with the oracle after every round: extreme bytes in both MMA operands, extreme carries in the plain products."""
@@ -391,7 +396,7 @@ def test_contraction_rounds_special_values_and_edge_challenges(orc, monkeypatch,
     rnd = random.Random(12)
     pool = [0, 1, pm.P - 1, 2, pm.P - 2, (1 << 248) - 1, pm.P >> 1]
     tables = [[rnd.choice(pool) for _ in range(1 << nv)] for _ in range(m)]
-    tables[2] = [pm.P - 1] * (1 << nv)   # Montgomery form of p-1 and near-maximal products everywhere
+    tables[m - 1] = [pm.P - 1] * (1 << nv)   # Montgomery form of p-1 and near-maximal products everywhere
     products = [(pm.P - 1, list(range(m)))]
     poly, opoly = both_polys(orc, nv, tables, products)
     st, ost = sc.IPForMLSumcheck.prover_init(poly), orc.Prover(opoly)
@@ -408,7 +413,7 @@ def test_contraction_rounds_special_values_and_edge_challenges(orc, monkeypatch,
     assert st.gemm_round_count() == 4   # rounds 1..4 of nv=11 (1024 .. 128 pairs)
 
 
-@pytest.mark.parametrize("nv,n_products,m", [(12, 1, 3), (13, 2, 3), (12, 1, 4)])
+@pytest.mark.parametrize("nv,n_products,m", [(12, 1, 3), (13, 2, 3), (12, 1, 4), (12, 1, 2)])
 def test_fold_rounds_launched_ahead_of_their_challenge(orc, monkeypatch, nv, n_products, m):
     """Inside a whole-proof call the next large fold round is launched right behind the current one and receives its challenge
     through mapped memory (gemm_prelaunch).  Same proof as the oracle's, as with SC_NO_PRELAUNCH=1, as through caller-driven rounds
@@ -443,7 +448,7 @@ def test_fold_rounds_launched_ahead_of_their_challenge(orc, monkeypatch, nv, n_p
     assert np.array_equal(ev2, want) and st2.launch_count() == launches
 
 
-@pytest.mark.parametrize("n_products,m", [(1, 3), (1, 4), (2, 3)])
+@pytest.mark.parametrize("n_products,m", [(1, 3), (1, 4), (2, 3), (1, 2)])
 def test_contraction_rounds_on_borrowed_device_tables(orc, monkeypatch, n_products, m):
     """sc_prover_create_device: the caller's tables already live in HBM and are borrowed, never written.  One product: the
     contraction kernels read them through descriptors built on the caller's pointers; several products: nothing can be

@@ -78,7 +78,7 @@ def test_single_process_sharded_contraction_rounds(orc, monkeypatch, world):
     monkeypatch.setenv("SC_RES_MAX_PAIRS", "64")
     monkeypatch.setenv("SC_REPL_LOG2", "8")   # stay sharded until the global tables are down to 2^8 elements
     devs = _devices(world)
-    for nv, n_products, seed, m in [(12, 1, 41, 3), (13, 3, 42, 3), (12, 2, 43, 4)]:
+    for nv, n_products, seed, m in [(12, 1, 41, 3), (13, 3, 42, 3), (12, 2, 43, 4), (12, 1, 44, 2)]:
         tabs, prods = _instance(orc, nv, n_products, m, seed)
         poly = sc.ListOfProductsOfPolynomials.new(nv)
         for c, ix in prods:
