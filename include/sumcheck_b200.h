@@ -144,7 +144,7 @@ SC_API uint64_t sc_prover_tc_round_count(const sc_prover *p);
  * sc_prove_round (caller-driven rounds) never uses it. */
 SC_API uint64_t sc_prover_resident_round_count(const sc_prover *p);
 /* ... and how many rounds ran on the tensor-core CONTRACTION kernels (csrc/gemm_sum.cuh): for lists whose products all have
- * three multiplicands (BASELINE configs 2 and 3) or all have four (config 4) the sum over the hypercube of prover.rs:110-148 is a u8 x u8 -> s32
+ * two (GKR phases), three (BASELINE configs 2 and 3) or four (config 4) multiplicands the sum over the hypercube of prover.rs:110-148 is a u8 x u8 -> s32
  * tcgen05.mma over the bytes of per-pair plain products; rounds with at least SC_TC_MIN_PAIRS pairs.  SC_NO_GEMM=1 disables it. */
 SC_API uint64_t sc_prover_gemm_round_count(const sc_prover *p);
 

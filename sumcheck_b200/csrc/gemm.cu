@@ -52,7 +52,7 @@ static int grid_for(uint32_t items, int G, int sms) {
 }
 
 // items a single launch may carry (every CTA at most MAX_ITEMS_PER_CTA per group)
-unsigned long long max_items_round1(int sms, int mm) { return (unsigned long long)sms * (mm == 2 ? 1 : G1) * MAX_ITEMS_PER_CTA; }
+unsigned long long max_items_round1(int sms, int mm) { return (unsigned long long)sms * (mm == 2 ? 2 : G1) * MAX_ITEMS_PER_CTA; }  // (mm = 2: two CTAs per SM)
 unsigned long long max_items_fold(int sms, int mm) { return (unsigned long long)sms * (mm == 4 ? GF4 : GF) * MAX_ITEMS_PER_CTA; }
 
 template <int TAG, int G, int MM>
@@ -76,7 +76,7 @@ cudaError_t launch_round1(const Params& P, int mm, int sms, cudaStream_t stream)
     if (mm == 2) {  // two-table products: TMA + MMA only
         cudaError_t e = prepare<7>(gemm_round1_raw_kernel<2>, RAW_SMEM);
         if (e != cudaSuccess) return e;
-        gemm_round1_raw_kernel<2><<<grid_for(P.items, 1, sms), RAW_THREADS, RAW_SMEM, stream>>>(P);
+        gemm_round1_raw_kernel<2><<<grid_for(P.items, 1, 2 * sms), RAW_THREADS, RAW_SMEM, stream>>>(P);
         return cudaGetLastError();
     }
     return mm == 4 ? launch_r1<3, G1, 4>(P, sms, stream) : launch_r1<1, G1, 3>(P, sms, stream);

@@ -638,11 +638,11 @@ __global__ void __launch_bounds__(G * 128 + 64, 1) gemm_round1_kernel(const Para
 // Both operands are the tables' tiles as TMA lands them (64-byte rows = one pair, SWIZZLE_64B): the kernel is a TMA warp, an MMA warp
 // and four warps that only run the epilogue — not one multiplication on the CUDA cores.  Items (tile, product) are dealt to the CTAs
 // round-robin; a ring of RAW_STAGES (X, Y) tile pairs.
-constexpr uint32_t RAW_STAGES = 8, RAW_STAGE_BYTES = 16384, RAW_THREADS = 192;
+constexpr uint32_t RAW_STAGES = 6, RAW_STAGE_BYTES = 16384, RAW_THREADS = 192;  // 96 KiB + 64 tensor-memory columns: two CTAs per SM
 constexpr size_t RAW_SMEM = (size_t)RAW_STAGES * RAW_STAGE_BYTES;
 
 template <int MM = 2>  // (a template only so that the header can be included by several translation units)
-__global__ void __launch_bounds__(RAW_THREADS, 1) gemm_round1_raw_kernel(const Params P) {
+__global__ void __launch_bounds__(RAW_THREADS, 2) gemm_round1_raw_kernel(const Params P) {
     static_assert(MM == 2, "two-table products");
     using S_ = Shape<2>;
     extern __shared__ __align__(1024) uint8_t smem[];
