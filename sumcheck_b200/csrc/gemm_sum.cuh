@@ -15,11 +15,16 @@
 // which the host evaluates at t = 0..d after reducing the six big integers mod p (host_fr.h gemm_finish) — all exact, so the
 // message is bit-identical to the reference's.  Per pair at degree 3: 192 IMAD.WIDE instead of 589 (round 1) / 573 (fold rounds).
 //
-// Kernel shape: ONE persistent CTA per SM = G compute groups of 128 threads (a group owns one 128-pair tile at a time) + two
-// producer warps.  Warp P0 stages tables with TMA and, in fold rounds, issues the fix_variables MMAs (tc_fold.cuh) into
-// per-group accumulators; warp P1 issues the contraction MMAs of every group into ONE accumulator set in tensor memory (a
-// single issuing thread keeps the accumulating MMAs ordered).  After its last tile a CTA adds the anti-diagonals of D
-// (sum over u+v = k) into 64-bit totals in global memory; the last CTA carries them into the six integers and publishes.
+// Products of FOUR tables use the same idea with both operands computed (X = three plain products of tables 0 and 1, Y = three of
+// tables 2 and 3: a 192 x 192 contraction, nine sums); products of TWO tables need no per-pair multiplication at all (X and Y are the
+// tables' own pairs).  See Shape<MM> below.
+//
+// Kernel shape: ONE persistent CTA per SM = G compute groups of 128 threads (a group owns one 128-pair tile at a time) + producer warps,
+// each a single thread: W_TMA stages table tiles, W_FOLD (fold rounds) issues the fix_variables MMAs (tc_fold.cuh) into per-group
+// accumulators in tensor memory, W_SUM issues the contraction MMAs of every group into ONE accumulator set (a single issuing thread
+// keeps the accumulating MMAs ordered).  After its last tile a CTA adds the anti-diagonals of D (sum over u+v = k) into 64-bit totals
+// in global memory; the last CTA carries them into the integers, exchanges them with the peer GPUs when the polynomial is sharded,
+// and publishes them to mapped host memory.  Inside whole-proof calls a fold round may be launched AHEAD of its challenge (PRE).
 #pragma once
 #include "kernels.cuh"
 #include "tc_fold.cuh"
