@@ -157,7 +157,8 @@ def _bench_single_process(args, cfg, nv, B):
         step_ms.append((time.perf_counter() - t0) * 1e3)
     ms_step = sum(step_ms) / len(step_ms)
     st.set_timing(True)
-    prove()
+    prove()  # (untimed) first instrumented proof: rounds that are otherwise launched ahead of their challenge run another build of
+    prove()  # the fold kernel when instrumented — its first launch loads the code; the per-round times come from the second proof
     st.set_timing(False)
     round_ms = st.round_times_ms().astype(np.float64)
     launches = st.launch_count()
@@ -241,7 +242,8 @@ def _bench_torchrun(args, cfg, nv, B):
 
     ms_step, step_ms = timed(prove)
     st.set_timing(True)
-    prove()
+    prove()  # (untimed) first instrumented proof: rounds that are otherwise launched ahead of their challenge run another build of
+    prove()  # the fold kernel when instrumented — its first launch loads the code; the per-round times come from the second proof
     st.set_timing(False)
     round_ms = st.round_times_ms().astype(np.float64)
     launches = st.launch_count()
