@@ -157,8 +157,7 @@ def _bench_single_process(args, cfg, nv, B):
         step_ms.append((time.perf_counter() - t0) * 1e3)
     ms_step = sum(step_ms) / len(step_ms)
     st.set_timing(True)
-    prove()  # (untimed) first instrumented proof: rounds that are otherwise launched ahead of their challenge run another build of
-    prove()  # the fold kernel when instrumented — its first launch loads the code; the per-round times come from the second proof
+    prove()
     st.set_timing(False)
     round_ms = st.round_times_ms().astype(np.float64)
     launches = st.launch_count()
@@ -242,8 +241,7 @@ def _bench_torchrun(args, cfg, nv, B):
 
     ms_step, step_ms = timed(prove)
     st.set_timing(True)
-    prove()  # (untimed) first instrumented proof: rounds that are otherwise launched ahead of their challenge run another build of
-    prove()  # the fold kernel when instrumented — its first launch loads the code; the per-round times come from the second proof
+    prove()
     st.set_timing(False)
     round_ms = st.round_times_ms().astype(np.float64)
     launches = st.launch_count()
