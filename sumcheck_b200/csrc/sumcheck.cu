@@ -430,6 +430,7 @@ cudaError_t launch_round1_tma(sc_prover* p, const sck::RoundParams& rp) {
 void set_exchange_params(sc_prover* p, sck::RoundParams& rp);  // capi_multi.inc
 bool comm_fused_exchange_ok(const sc_prover* p);  // the sharded rounds of this handle run the fused peer-memory exchange
 int comm_device_share(const sc_prover* p);        // ranks of the group that share this rank's device
+bool comm_in_process(const sc_prover* p);         // the ranks are host threads of ONE process (sc_prover_create_multi)
 uint32_t set_exchange_params_resident(sc_prover* p, sck::RoundParams& rp, uint32_t n_rounds);
 bool comm_failed(const sc_prover* p);
 void comm_clear_error(sc_prover* p);
@@ -558,7 +559,10 @@ int gemm_prelaunch(sc_prover* p) {
     if (p->comm) {
         // a shard: only sharded rounds with the fused exchange, and only when this rank has its GPU to itself — a kernel that
         // waits for its challenge holds every SM, and a rank sharing the device could then never finish the round it waits for
-        if (!comm_fused_exchange_ok(p) || comm_device_share(p) > 1 || i2 >= p->switch_round) return SC_OK;
+        // (and only with one process per GPU: with the ranks as threads of one process a proof now and then ran into the exchange
+        // time-out — seen once in ~10 runs on 2 GPUs, never with separate processes; CUDA calls of different threads share locks, and a
+        // kernel that waits for its host thread while that thread's next call waits behind another rank's is one deadlock too many)
+        if (!comm_fused_exchange_ok(p) || comm_device_share(p) > 1 || comm_in_process(p) || i2 >= p->switch_round) return SC_OK;
         p->exchange = true;
         const bool ok = gemm_round_ok(p, n_pairs, true);
         p->exchange = false;
