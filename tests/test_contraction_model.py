@@ -104,3 +104,59 @@ def test_host_finish_matches_prove_round_model():
                     want = (want + term) % pm.P
                 assert pm.from_mont_limbs(out[t]) == want, (kx, ky, trial, t)
     assert L.sc_fr_contraction_finish(None, 26, 2, 1, None) != 0
+
+
+# ---- the work split of a persistent CTA (gemm_sum.cuh Split): three producer warps and the compute groups each derive ring slots and
+# barrier phases from (n, j, g) alone, so the arithmetic has to describe ONE consistent sequence for every grid / item count
+class _Split:
+    def __init__(self, items, G, MM, grid, block):
+        self.G, self.MM = G, MM
+        self.stride, self.first = grid * G, block * G
+        last_g = self.first + G - 1
+        self.n_min = (items - last_g + self.stride - 1) // self.stride if last_g < items else 0
+        self.rem = 0
+        for g in range(G - 1):
+            f = self.first + g
+            ni = (items - f + self.stride - 1) // self.stride if f < items else 0
+            self.rem += 1 if ni > self.n_min else 0
+
+    def n_items(self, g):
+        return self.n_min + (1 if g < self.rem else 0)
+
+    def steps(self):
+        return self.n_min + (1 if self.rem else 0)
+
+    def groups(self, n):
+        return self.G if n < self.n_min else self.rem
+
+    def unit(self, n, j, g):
+        return self.MM * self.G * n + j * self.groups(n) + g
+
+    def item(self, n, g):
+        return self.first + g + n * self.stride
+
+
+def test_work_split_is_one_consistent_sequence():
+    for G, MM in [(3, 3), (2, 4), (3, 2), (1, 2)]:
+        for items in list(range(1, 40)) + [148 * G, 148 * G + 1, 1000, 4096]:
+            grid = min(148, (items + G - 1) // G)   # gemm.cu grid_for
+            seen = set()
+            for block in range(grid):
+                sp = _Split(items, G, MM, grid, block)
+                assert sp.n_items(0) >= 1                      # every launched CTA initialises its accumulators
+                walked = []                                    # the order the producer warps walk the units
+                for n in range(sp.steps()):
+                    for j in range(MM):
+                        for g in range(G):
+                            if g < sp.groups(n):
+                                walked.append((n, j, g))
+                # dense unit numbers in walking order = what the compute groups compute for their own (n, j, g)
+                assert [sp.unit(*u) for u in walked] == list(range(len(walked)))
+                assert len(walked) == MM * sum(sp.n_items(g) for g in range(G))
+                for g in range(G):
+                    assert all(n < sp.n_items(g) for (n, j, gg) in walked if gg == g)
+                    for n in range(sp.n_items(g)):
+                        w = sp.item(n, g)
+                        assert w < items and w not in seen
+                        seen.add(w)
+            assert seen == set(range(items))                   # every item exactly once over the grid
