@@ -434,6 +434,8 @@ __device__ __forceinline__ void epilogue(const Params& P, uint32_t tmem_d, bool 
     __syncthreads();
     if (tid >= 32) return;
     constexpr uint32_t NW = NB * OUT_LIMBS;
+    static_assert(2 * NW <= sck::MAIL_WORDS, "a rank's integers must fit its mailbox slot ({limb, sequence number} pairs)");
+    static_assert(NW < OUT_SLOT_WORDS - 40, "the integers must leave room for the challenge words and the flag in the result slot");
     if (P.rp.peer_mail) {
         // sharded polynomial: all-to-all of the integers over NVLink peer memory — every limb ONE 8-byte {limb, sequence
         // number} store into the receiver's mailbox (kernels.cuh mail_store: single-copy atomic), then the integer sums over
